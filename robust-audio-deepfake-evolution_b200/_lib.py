@@ -1,0 +1,95 @@
+"""ctypes binding of libbimamba_sm100.so (the C ABI declared in include/bimamba.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbimamba_sm100.so")
+
+F32, BF16, F16 = 0, 1, 2
+FLAG_SOFTPLUS = 1
+FLAG_SILU = 1
+ABI_VERSION = 1
+
+EXPORTS = (
+    "bimamba_abi_version", "bimamba_last_error", "bimamba_scan_plan",
+    "bimamba_selective_scan_fwd", "bimamba_selective_scan_bwd",
+    "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_reduce_partials",
+)
+
+
+class ScanDesc(C.Structure):
+    """Mirror of `struct bimamba_scan_desc` (include/bimamba.h)."""
+    _fields_ = (
+        [(n, C.c_void_p) for n in (
+            "u", "delta", "z", "Bm", "Cm", "A", "D", "delta_bias", "out", "ckpt",
+            "dout", "du", "ddelta", "dz", "dBC_part", "dA_part", "dD_part", "dbias_part")]
+        + [(n, C.c_int32) for n in (
+            "batch", "ndir", "dim", "seqlen", "dstate", "io_dtype", "bc_dtype", "flags",
+            "chunk_items", "group_channels", "pad_to", "reserved0")]
+        + [(n, C.c_int64) for n in (
+            "u_bs", "u_ds", "u_rs", "delta_bs", "delta_ds", "delta_rs", "z_bs", "z_ds", "z_rs",
+            "bc_bs", "bc_ds", "bc_rs", "out_bs", "out_ds", "out_rs", "dz_bs", "dz_ds", "dz_rs", "dbc_rs")]
+    )
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load (once) and type the library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` or "
+                "`python robust-audio-deepfake-evolution_b200/build.py` (needs nvcc). "
+                "There is no CPU fallback for the Bi-Mamba path.")
+        lib = C.CDLL(LIB_PATH)
+        i32, i64, vp = C.c_int, C.c_int64, C.c_void_p
+        lib.bimamba_abi_version.restype = i32
+        lib.bimamba_abi_version.argtypes = []
+        lib.bimamba_last_error.restype = C.c_char_p
+        lib.bimamba_last_error.argtypes = []
+        lib.bimamba_scan_plan.restype = i32
+        lib.bimamba_scan_plan.argtypes = [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        for name in ("bimamba_selective_scan_fwd", "bimamba_selective_scan_bwd"):
+            fn = getattr(lib, name)
+            fn.restype = i32
+            fn.argtypes = [C.POINTER(ScanDesc), vp]
+        lib.bimamba_causal_conv1d_fwd.restype = i32
+        lib.bimamba_causal_conv1d_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
+                                                  i64, i64, i64, i64, i64, i32, i32, vp]
+        lib.bimamba_causal_conv1d_bwd.restype = i32
+        lib.bimamba_causal_conv1d_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
+                                                  i64, i64, i64, i64, i64, i64, i64, i32, i32, vp]
+        lib.bimamba_reduce_partials.restype = i32
+        lib.bimamba_reduce_partials.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp]
+        got = lib.bimamba_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"libbimamba ABI {got} != expected {ABI_VERSION}; rebuild the library")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().bimamba_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def scan_plan(seqlen: int, dim: int, rows: int, backward: bool = False):
+    """-> (chunk_items, group_channels, nchunks)"""
+    ci, gc = C.c_int(0), C.c_int(0)
+    n = load().bimamba_scan_plan(int(seqlen), int(dim), int(rows), int(backward), C.byref(ci), C.byref(gc))
+    return ci.value, gc.value, n

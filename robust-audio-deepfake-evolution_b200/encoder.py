@@ -1,0 +1,60 @@
+"""`PN_BiMambas_Encoder` and the 4-layer backend with the reference's attribute names
+(src/models/DualStreamSEMamba.py:445-486, :697-710, :755-767), on top of the fused Bi-Mamba block."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .mamba_simple import Mamba
+
+
+class PN_BiMambas_Encoder(nn.Module):
+    """Pre-norm Bi-Mamba layer.  Same constructor, attributes (`mamba`, `norm1`, `norm2`,
+    `feed_forward`) and state_dict keys as DualStreamSEMamba.py:451-465."""
+
+    def __init__(self, d_model, n_state):
+        super().__init__()
+        self.d_model = d_model
+        self.mamba = Mamba(d_model, n_state)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.feed_forward = nn.Sequential(
+            nn.Linear(d_model, d_model * 4),
+            nn.GELU(),
+            nn.Linear(d_model * 4, d_model),
+        )
+
+    def forward(self, x):
+        residual = x
+        x_norm = self.norm1(x)                                   # :472
+        mamba_out = self.mamba.forward_bidirectional(x_norm)     # :473-481 in one fused pass
+        mamba_out = self.norm2(mamba_out)                        # :482
+        ff_out = self.feed_forward(mamba_out)                    # :483
+        return ff_out + residual                                 # :485
+
+
+class BiMambaBackend(nn.Module):
+    """The part of the reference `Model` after fusion (DualStreamSEMamba.py:697-710, :755-767):
+    `backbone_layers`, `norm_f`, `attention_pool`, `dropout`, `classifier` with the same names."""
+
+    def __init__(self, emb_size=144, num_encoders=4, d_state=16):
+        super().__init__()
+        self.backbone_layers = nn.ModuleList(
+            [PN_BiMambas_Encoder(d_model=emb_size, n_state=d_state) for _ in range(num_encoders)])
+        self.norm_f = nn.LayerNorm(emb_size)
+        self.attention_pool = nn.Linear(emb_size, 1)
+        self.dropout = nn.Dropout(0.1)
+        self.classifier = nn.Linear(emb_size, 2)
+
+    def forward_features(self, f_fused):
+        for layer in self.backbone_layers:
+            f_fused = layer(f_fused)
+        return f_fused
+
+    def forward(self, f_fused):
+        f_fused = self.norm_f(self.forward_features(f_fused))                       # :759
+        attn = F.softmax(self.attention_pool(f_fused), dim=1)                       # :762
+        features = torch.matmul(attn.transpose(1, 2), f_fused).squeeze(1)           # :763
+        features = self.dropout(features)                                           # :764
+        return features, self.classifier(features)                                  # :767

@@ -1,0 +1,172 @@
+"""GPU parity of the Bi-Mamba block / encoder / backend against the oracle and the golden
+fixtures generated from the reference (tests/golden/make_golden.py).
+
+Tolerance (north_star): <= 1e-4 relative fp32, <= 2e-2 bf16, outputs AND every gradient.
+"""
+import copy
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import bimamba_b200 as bm
+from oracle import bimamba_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _load_mamba(m, params):
+    sd = {k: torch.as_tensor(np.asarray(v)).float() for k, v in params.items()}
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+
+
+@pytest.mark.parametrize("tag", ["small", "phase6"])
+def test_mamba_forward_backward_vs_reference_fixture(golden_dir, tag):
+    """Mamba.forward (one direction) against the reference's own MambaBlock run (fixture)."""
+    g = dict(np.load(os.path.join(golden_dir, f"mamba_block_{tag}.npz")))
+    params = {k[len("param."):]: v for k, v in g.items() if k.startswith("param.")}
+    d_model = g["x"].shape[-1]
+    m = bm.Mamba(d_model, 16).cuda()
+    _load_mamba(m, params)
+    x = torch.tensor(g["x"], device="cuda", requires_grad=True)
+    out = m(x)
+    assert rel(out, g["out"]) < 1e-4
+    out.backward(torch.tensor(g["cot"], device="cuda"))
+    assert rel(x.grad, g["grad.x"]) < 1e-4
+    for name, p in m.named_parameters():
+        assert rel(p.grad, g["grad." + name]) < 1e-4, name
+
+
+def test_encoder_vs_reference_fixture(golden_dir):
+    """PN_BiMambas_Encoder (both directions, LN, FFN, residual) against the reference class."""
+    g = dict(np.load(os.path.join(golden_dir, "pn_bimamba_encoder_phase6.npz")))
+    enc = bm.PN_BiMambas_Encoder(144, 16).cuda()
+    sd = {k[len("param."):]: torch.tensor(v).float() for k, v in g.items() if k.startswith("param.")}
+    enc.load_state_dict(sd, strict=True)
+    x = torch.tensor(g["x"], device="cuda", requires_grad=True)
+    out = enc(x)
+    assert rel(out, g["out"]) < 1e-4
+    out.backward(torch.tensor(g["cot"], device="cuda"))
+    assert rel(x.grad, g["grad.x"]) < 1e-4
+    for name, p in enc.named_parameters():
+        assert rel(p.grad, g["grad." + name]) < 1e-4, name
+
+
+@pytest.mark.parametrize("Bsz,L", [(3, 201), (2, 499), (1, 1), (2, 260)])
+def test_bidirectional_block_fp32_vs_oracle(Bsz, L):
+    p64 = orc.init_mamba_params(144, 16, seed=L, dtype=torch.float64)
+    m = bm.Mamba(144, 16).cuda()
+    _load_mamba(m, {k: v.numpy() for k, v in p64.items()})
+    g = torch.Generator().manual_seed(L)
+    x = torch.randn(Bsz, L, 144, generator=g)
+    cot = torch.randn(Bsz, L, 144, generator=g)
+    pr = {k: v.float().double().requires_grad_(True) for k, v in p64.items()}
+    xr = x.double().requires_grad_(True)
+    ref = orc.bimamba_ref(pr, xr)
+    (ref * cot.double()).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    out = m.forward_bidirectional(xd)
+    out.backward(cot.cuda())
+    assert rel(out, ref) < 1e-4
+    assert rel(xd.grad, xr.grad) < 1e-4
+    for name, prm in m.named_parameters():
+        assert rel(prm.grad, pr[name].grad) < 1e-4, name
+
+
+def test_block_bf16_autocast_vs_oracle():
+    """Config-2 numerics: bf16 activations / fp32 state under autocast; oracle in fp64 on the same
+    fp32 master weights.  Tolerance 2e-2 relative."""
+    p64 = orc.init_mamba_params(144, 16, seed=2, dtype=torch.float64)
+    m = bm.Mamba(144, 16).cuda()
+    _load_mamba(m, {k: v.numpy() for k, v in p64.items()})
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(4, 201, 144, generator=g)
+    cot = torch.randn(4, 201, 144, generator=g)
+    pr = {k: v.float().double().requires_grad_(True) for k, v in p64.items()}
+    xr = x.double().requires_grad_(True)
+    ref = orc.bimamba_ref(pr, xr)
+    (ref * cot.double()).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m.forward_bidirectional(xd)
+    assert out.dtype == torch.bfloat16
+    out.float().backward(cot.cuda())
+    assert rel(out, ref) < 2e-2
+    assert rel(xd.grad, xr.grad) < 2e-2
+    for name, prm in m.named_parameters():
+        assert prm.grad.dtype == torch.float32
+        assert rel(prm.grad, pr[name].grad) < 2e-2, name
+
+
+def test_fusion_identities_on_device():
+    """Size-independent properties at the Phase-6 training shape (B=64, L=201):
+    bidirectional(x) == fwd(x) + flip(fwd(flip(x)))  (DualStreamSEMamba.py:473-481)."""
+    torch.manual_seed(0)
+    m = bm.Mamba(144, 16).cuda()
+    with torch.no_grad():
+        m.A_log.add_(0.1 * torch.randn_like(m.A_log))
+    x = torch.randn(64, 201, 144, device="cuda")
+    with torch.no_grad():
+        bi = m.forward_bidirectional(x)
+        two = m(x) + torch.flip(m(torch.flip(x, dims=[1])), dims=[1])
+    assert rel(bi, two) < 1e-5
+
+
+def test_eer_identity_on_synthetic_scoring_set():
+    """Identical EER on a fixed synthetic scoring set (fp32): scores = logits[:, 1] of the 4-layer
+    backend + head (DualStreamSEMamba.py:755-767, main.py:978-984), EER by evaluation.py:154-160."""
+    n_utt, L = 192, 64
+    layers = [orc.init_encoder_params(144, 16, seed=10 + i) for i in range(4)]
+    head = orc.init_head_params(144, seed=3)
+    g = torch.Generator().manual_seed(77)
+    feats = torch.randn(n_utt, L, 144, generator=g)
+    labels = (torch.rand(n_utt, generator=g) < 0.3).numpy()
+    with torch.no_grad():
+        _, logits_ref = orc.backend_ref(layers, head, feats)
+    net = bm.BiMambaBackend(144, 4, 16).cuda().eval()
+    sd = {}
+    for i, p in enumerate(layers):
+        for k, v in p.items():
+            sd[f"backbone_layers.{i}.{k}"] = v
+    sd.update(head)
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        _, logits = net(feats.cuda())
+    s_ref = logits_ref[:, 1].numpy().astype(np.float64)
+    s_dev = logits[:, 1].cpu().numpy().astype(np.float64)
+    eer_ref, _ = orc.compute_eer_ref(s_ref[labels], s_ref[~labels])
+    eer_dev, _ = orc.compute_eer_ref(s_dev[labels], s_dev[~labels])
+    assert np.abs(s_ref - s_dev).max() < 1e-4 * max(1.0, np.abs(s_ref).max())
+    assert eer_dev == eer_ref
+
+
+def test_module_surface():
+    """deepcopy (EMA AveragedModel, main.py:495), pickle, no_grad / inference_mode
+    (filter_dirty_data.py:134-151), frozen params, clip_grad_norm_ (main.py:1104)."""
+    m = bm.PN_BiMambas_Encoder(144, 16).cuda()
+    m2 = copy.deepcopy(m)
+    m3 = pickle.loads(pickle.dumps(m))
+    x = torch.randn(2, 33, 144, device="cuda")
+    with torch.inference_mode():
+        a, b, c = m(x), m2(x), m3(x)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    for p in m.mamba.parameters():
+        p.requires_grad_(False)
+    y = m(x.requires_grad_(True))
+    y.sum().backward()
+    assert x.grad is not None and all(p.grad is None for p in m.mamba.parameters())
+    for p in m.mamba.parameters():
+        p.requires_grad_(True)
+    m(x).sum().backward()
+    torch.nn.utils.clip_grad_norm_(m.parameters(), 3.0)
+    with torch.autocast("cuda", dtype=torch.float16):
+        assert m(x).isfinite().all()

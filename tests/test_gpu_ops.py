@@ -1,0 +1,157 @@
+"""GPU parity of the op-level kernels (through the C ABI) against the CPU oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: <= 1e-4 relative in fp32,
+<= 2e-2 in bf16 (fp32 state), measured as max|a-b| / max|b| against the fp64 oracle.
+"""
+import pytest
+import torch
+
+import bimamba_b200 as bm
+from oracle import bimamba_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2, torch.float16: 5e-3}
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _scan_inputs(Bsz, D, L, N=16, seed=0, dtype=torch.float32):
+    """SURVEY 8(d) config-5 distributions (trained-like A, mamba dt-bias range)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(Bsz, D, L, generator=g)
+    delta = 0.5 * torch.randn(Bsz, D, L, generator=g)
+    z = torch.randn(Bsz, D, L, generator=g)
+    Bm = torch.randn(Bsz, N, L, generator=g)
+    Cm = torch.randn(Bsz, N, L, generator=g)
+    A = -torch.exp(torch.log(torch.arange(1, N + 1, dtype=torch.float32)).repeat(D, 1)
+                   + 0.1 * torch.randn(D, N, generator=g))
+    Dp = 1 + 0.1 * torch.randn(D, generator=g)
+    dt = torch.exp(torch.rand(D, generator=g) * (torch.log(torch.tensor(0.1)) - torch.log(torch.tensor(1e-3)))
+                   + torch.log(torch.tensor(1e-3)))
+    bias = dt + torch.log(-torch.expm1(-dt))
+    act = [t.to(dtype) for t in (u, delta, z, Bm, Cm)]
+    return act + [A, Dp, bias]
+
+
+def _run_both(Bsz, D, L, dtype, with_z=True, with_D=True, with_bias=True, softplus=True, seed=0):
+    u, delta, z, Bm, Cm, A, Dp, bias = _scan_inputs(Bsz, D, L, seed=seed, dtype=dtype)
+    if not softplus:          # a raw delta must be a positive step size
+        delta = (0.2 * delta.float().abs()).to(dtype)
+        bias = bias.abs()
+    names = ["u", "delta", "A", "B", "C", "D", "z", "bias"]
+    cpu = [u, delta, A, Bm, Cm, Dp if with_D else None, z if with_z else None, bias if with_bias else None]
+    # oracle in fp64 on the (dtype-rounded) inputs
+    ref_in = [None if t is None else t.double().requires_grad_(True) for t in cpu]
+    ref = orc.selective_scan_ref(*ref_in, delta_softplus=softplus)
+    g = torch.Generator().manual_seed(seed + 1)
+    cot = torch.randn(ref.shape, generator=g).to(dtype)
+    (ref * cot.double()).sum().backward()
+    dev_in = [None if t is None else t.cuda().requires_grad_(True) for t in cpu]
+    out = bm.selective_scan_fn(*dev_in, delta_softplus=softplus)
+    assert out.dtype == dtype and out.shape == ref.shape
+    out.backward(cot.cuda())
+    torch.cuda.synchronize()
+    errs = {"out": rel(out, ref)}
+    for n, a, b in zip(names, dev_in, ref_in):
+        if a is not None:
+            errs["d" + n] = rel(a.grad, b.grad)
+    return errs
+
+
+@pytest.mark.parametrize("L", [1, 5, 32, 33, 64, 201, 224, 256])
+def test_scan_single_chunk_fp32(L):
+    errs = _run_both(2, 40, L, torch.float32)
+    assert max(errs.values()) < TOL[torch.float32], errs
+
+
+@pytest.mark.parametrize("L", [257, 300, 499, 777, 1024])
+def test_scan_multi_chunk_fp32(L):
+    errs = _run_both(2, 24, L, torch.float32, seed=L)
+    assert max(errs.values()) < TOL[torch.float32], errs
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("L", [201, 499])
+def test_scan_half_precision_io(dtype, L):
+    errs = _run_both(2, 48, L, dtype, seed=3)
+    assert max(errs.values()) < TOL[dtype], errs
+
+
+@pytest.mark.parametrize("with_z,with_D,with_bias,softplus", [
+    (False, True, True, True), (True, False, True, True), (True, True, False, True),
+    (True, True, True, False), (False, False, False, False)])
+def test_scan_optional_operands(with_z, with_D, with_bias, softplus):
+    errs = _run_both(3, 17, 77, torch.float32, with_z, with_D, with_bias, softplus, seed=5)
+    assert max(errs.values()) < TOL[torch.float32], errs
+
+
+def test_scan_wide_and_ragged_channels():
+    # dim = 288 (Phase 6) and a dim that is not a multiple of the channel group
+    for D in (288, 37):
+        errs = _run_both(2, D, 201, torch.float32, seed=D)
+        assert max(errs.values()) < TOL[torch.float32], (D, errs)
+
+
+def test_scan_empty():
+    u = torch.zeros(0, 8, 16, device="cuda")
+    out = bm.selective_scan_fn(u, u, -torch.ones(8, 16, device="cuda"), torch.zeros(0, 16, 16, device="cuda"),
+                               torch.zeros(0, 16, 16, device="cuda"))
+    assert out.shape == (0, 8, 16)
+
+
+def test_scan_long_against_oracle_on_gpu():
+    """Config-5 length (L = 8192): the oracle's sequential loop is run on the GPU in fp64
+    (same oracle code, device-agnostic) because 8192 python steps on CPU tensors are slow."""
+    u, delta, z, Bm, Cm, A, Dp, bias = _scan_inputs(2, 64, 8192, seed=9)
+    dev = [t.cuda() for t in (u, delta, A, Bm, Cm, Dp, z, bias)]
+    ref = orc.selective_scan_ref(*[t.double() for t in dev], delta_softplus=True)
+    out = bm.selective_scan_fn(*dev, delta_softplus=True)
+    assert rel(out, ref) < TOL[torch.float32]
+
+
+def test_scan_rejects_cpu_and_bad_state():
+    u = torch.zeros(1, 8, 16)
+    with pytest.raises(RuntimeError):
+        bm.selective_scan_fn(u, u, -torch.ones(8, 16), torch.zeros(1, 16, 16), torch.zeros(1, 16, 16))
+    uc = u.cuda()
+    with pytest.raises(NotImplementedError):
+        bm.selective_scan_fn(uc, uc, -torch.ones(8, 8).cuda(), torch.zeros(1, 8, 16).cuda(), torch.zeros(1, 8, 16).cuda())
+
+
+# ---------------------------------------------------------------- conv
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("L", [1, 3, 8, 201, 300])
+@pytest.mark.parametrize("act", [None, "silu"])
+def test_causal_conv1d(dtype, L, act):
+    g = torch.Generator().manual_seed(L)
+    Bsz, D, K = 3, 20, 4
+    x = torch.randn(Bsz, D, L, generator=g).to(dtype)
+    w = torch.randn(D, K, generator=g) * 0.5
+    b = torch.randn(D, generator=g) * 0.5
+    cot = torch.randn(Bsz, D, L, generator=g).to(dtype)
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = orc.causal_conv1d_ref(xr, wr, br, act)
+    (ref * cot.double()).sum().backward()
+    xd, wd, bd = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    out = bm.causal_conv1d_fn(xd, wd, bd, activation=act)
+    out.backward(cot.cuda())
+    tol = TOL[dtype]
+    assert rel(out, ref) < tol
+    assert rel(xd.grad, xr.grad) < tol
+    assert rel(wd.grad, wr.grad) < tol
+    assert rel(bd.grad, br.grad) < tol
+
+
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_causal_conv1d_widths_no_bias(K):
+    g = torch.Generator().manual_seed(K)
+    x = torch.randn(2, 9, 50, generator=g)
+    w = torch.randn(9, K, generator=g)
+    ref = orc.causal_conv1d_ref(x.double(), w.double(), None, "silu")
+    out = bm.causal_conv1d_fn(x.cuda(), w.cuda(), None, activation="silu")
+    assert rel(out, ref) < 1e-5
