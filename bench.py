@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""Benchmark of the Bi-Mamba backend hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload at N = 1 is BASELINE.json configs[1]: the 4-layer Bi-Mamba backend (4 x
+PN_BiMambas_Encoder, d_model 144, d_state 16) fwd + bwd (+ AdamW step), 201 frames, batch 64,
+bf16 activations / fp32 state / fp32 master weights, synthetic WavLM-shaped features.  For N > 1
+(launched with torchrun, one rank per GPU) every rank runs that same per-GPU batch (weak scaling)
+and gradients are all-reduced over NCCL once per step.
+
+One JSON line is printed by rank 0.  `value` is device-resident throughput (inputs already in HBM,
+CUDA-graph replay, CUDA events, L2 flushed between steps); `e2e` is the same metric through the
+public API with the step's input coming from pinned HOST memory and the loss read back to the host
+every step.  `--impl reference` times the CPU oracle port of the reference's own path
+(oracle/bimamba_oracle.py; the reference is a Python package whose /root/reference tree does not
+exist on the GPU box) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+D_MODEL, D_STATE, N_LAYERS = 144, 16, 4
+D_INNER = 2 * D_MODEL
+METRIC = "bimamba_backend_fwd_bwd_frames_per_sec"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (config 2: 64)")
+    ap.add_argument("--frames", type=int, default=201)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scan sweep points")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"Phase-6 Bi-Mamba backend ({N_LAYERS} x PN_BiMambas_Encoder, d_model {D_MODEL}, d_state {D_STATE}) "
+                    f"fwd+bwd+AdamW training step, {args.frames} frames, batch {args.batch} per GPU "
+                    f"(BASELINE.json configs[1])",
+        "per_gpu_batch": args.batch, "global_batch": args.batch * world, "frames": args.frames,
+        "parallelism": f"dp{world}" if world > 1 else "single",
+    }
+
+
+# --------------------------------------------------------------------------------------
+# CPU oracle legs
+# --------------------------------------------------------------------------------------
+def oracle_step_fn(batch, frames):
+    """fwd+bwd of the 4-layer backend with the oracle port (fp32, all host threads)."""
+    from oracle import bimamba_oracle as orc
+    torch.manual_seed(1234)                      # reference default seed, src/main.py:1145
+    layers = []
+    for i in range(N_LAYERS):
+        p = orc.init_encoder_params(D_MODEL, D_STATE, seed=i, dtype=torch.float32)
+        layers.append({k: v.requires_grad_(True) for k, v in p.items()})
+    x = torch.randn(batch, frames, D_MODEL)
+
+    def step():
+        h = x
+        for p in layers:
+            h = orc.pn_bimamba_encoder_ref(p, h)
+        loss = h.square().mean()
+        loss.backward()
+        for p in layers:
+            for v in p.values():
+                v.grad = None
+        return float(loss)
+    return step
+
+
+def run_cpu_baseline(frames, sample_batch=8, reps=2):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = oracle_step_fn(sample_batch, frames)
+    step()                                        # warm-up
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        best = min(best, time.perf_counter() - t0)
+    return {
+        "value": sample_batch * frames / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "sample": f"oracle/bimamba_oracle.py (port of mamba_block.py + PN_BiMambas_Encoder), fp32, batch {sample_batch} "
+                  f"of the workload's batch, {frames} frames, {N_LAYERS} layers, fwd+bwd, best of {reps} after 1 warm-up "
+                  f"({best:.2f} s per sample step)",
+    }
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_batch = 8
+    step = oracle_step_fn(sample_batch, args.frames)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 8))            # bounded: each sample step is ~1-2 s of CPU work
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = sample_batch * args.frames * steps / dt
+    sample = (f"oracle port of the reference's CPU path (the reference is Python and /root/reference is absent on the GPU "
+              f"box), fp32, batch {sample_batch} sample of batch {args.batch}, {args.frames} frames, fwd+bwd, "
+              f"{steps} timed steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU legs
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class EventTimer:
+    """kernel_timer hook: CUDA events on the launching stream around each enqueue of one kernel."""
+
+    def __init__(self):
+        self.pairs = {}
+
+    def __call__(self, name):
+        timer = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.s = torch.cuda.Event(enable_timing=True)
+                self_inner.e = torch.cuda.Event(enable_timing=True)
+                self_inner.s.record()
+                return self_inner
+
+            def __exit__(self_inner, *a):
+                self_inner.e.record()
+                timer.pairs.setdefault(name, []).append((self_inner.s, self_inner.e))
+                return False
+        return _Ctx()
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: [s.elapsed_time(e) for s, e in v] for k, v in self.pairs.items()}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def scan_bytes(frames, ndir, esize, backward):
+    """fwd (4 D + 2 N) s, bwd (7 D + 4 N) s bytes per frame per direction."""
+    per = (7 * D_INNER + 4 * D_STATE) if backward else (4 * D_INNER + 2 * D_STATE)
+    return frames * ndir * per * esize
+
+
+def scan_sweep(bm, peak):
+    """Config-5 points: single-direction selective_scan op, 524 288 frames, D=288, N=16."""
+    out = []
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for dtype, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        for L in (256, 2048):
+            Bsz = (1 << 19) // L
+            u = torch.randn(Bsz, D_INNER, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            delta = (0.5 * torch.randn(Bsz, D_INNER, L, device="cuda", generator=g)).to(dtype).requires_grad_(True)
+            z = torch.randn(Bsz, D_INNER, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            Bm = torch.randn(Bsz, D_STATE, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            Cm = torch.randn(Bsz, D_STATE, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            A = (-torch.exp(torch.log(torch.arange(1, D_STATE + 1, device="cuda", dtype=torch.float32)).repeat(D_INNER, 1)
+                            + 0.1 * torch.randn(D_INNER, D_STATE, device="cuda", generator=g))).requires_grad_(True)
+            Dp = (1 + 0.1 * torch.randn(D_INNER, device="cuda", generator=g)).requires_grad_(True)
+            dt0 = torch.exp(torch.rand(D_INNER, device="cuda", generator=g) * (math.log(0.1) - math.log(1e-3)) + math.log(1e-3))
+            bias = (dt0 + torch.log(-torch.expm1(-dt0))).requires_grad_(True)     # mamba dt-bias init range
+            cot = torch.randn(Bsz, D_INNER, L, device="cuda", generator=g).to(dtype)
+            timer = EventTimer()
+            bm._lib.kernel_timer = timer
+            for it in range(5):
+                o = bm.selective_scan_fn(u, delta, A, Bm, Cm, Dp, z, bias, True)
+                o.backward(cot)
+                for t in (u, delta, z, Bm, Cm, A, Dp, bias):
+                    t.grad = None
+            bm._lib.kernel_timer = None
+            times = timer.summary()
+            es = 4 if dtype == torch.float32 else 2
+            for kname, bwd in (("scan_fwd", False), ("scan_bwd", True)):
+                ms = statistics.median(times[kname][2:])
+                gbs = scan_bytes(Bsz * L, 1, es, bwd) / (ms * 1e-3) / 1e9
+                out.append({"kernel": kname, "io": name, "L": L, "batch": Bsz, "ms": round(ms, 4),
+                            "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+            del u, delta, z, Bm, Cm, cot, o
+            torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the Bi-Mamba path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import bimamba_b200 as bm
+
+    torch.manual_seed(1234)
+    model = bm.BiMambaBackend(D_MODEL, N_LAYERS, D_STATE).cuda()
+    with torch.no_grad():                         # trained-like A (no power structure), SURVEY 8d
+        for layer in model.backbone_layers:
+            layer.mamba.A_log.add_(0.1 * torch.randn_like(layer.mamba.A_log))
+    params = list(model.backbone_layers.parameters())
+    bucket = bm.FlatGradBucket(params)
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4, capturable=True, fused=True)
+
+    B, L = args.batch, args.frames
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, L, D_MODEL, generator=gen).pin_memory()
+    x_dev = x_host.cuda()
+
+    def fwd_loss(x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model.forward_features(x)
+        return out.float().square().mean()
+
+    use_graph = not args.no_graph
+    if use_graph and world == 1:
+        runner = bm.GraphedTrainStep(fwd_loss, x_dev, bucket.zero, opt, warmup=3)
+
+        def step(x=None):
+            return runner.run(x)
+    elif use_graph:
+        runner = bm.GraphedTrainStep(fwd_loss, x_dev, bucket.zero, None, warmup=3)
+
+        def step(x=None):
+            loss = runner.run(x)
+            bucket.all_reduce_mean()
+            opt.step()
+            return loss
+    else:
+        def step(x=None):
+            bucket.zero()
+            loss = fwd_loss(x_dev if x is None else x.cuda(non_blocking=True))
+            loss.backward()
+            bucket.all_reduce_mean()
+            opt.step()
+            return loss
+
+    # count our own kernels in one eager step (the graph replays exactly these)
+    bm._lib.launch_count = 0
+    bucket.zero()
+    fwd_loss(x_dev).backward()
+    torch.cuda.synchronize()
+    launches_per_step = bm._lib.launch_count
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    # ---- device-resident timing: per-step CUDA events, L2 flushed (untimed) between steps ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    K = args.steps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for s, e in evs:
+        flush.zero_()
+        s.record()
+        step()
+        e.record()
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host input -> H2D -> step -> loss.item() every step ----
+    for _ in range(2):
+        float(step(x_host))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loss_val = float(step(x_host))            # .item(): D2H read + host sync, like src/main.py:1123
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    frames_total = B * L * world * K
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (scan backward), instrumented eager pass of the same steps ----
+        peak, peak_src = load_peaks()
+        timer = EventTimer()
+        bm._lib.kernel_timer = timer
+        for _ in range(3):
+            flush.zero_()
+            bucket.zero()
+            fwd_loss(x_dev).backward()
+        bm._lib.kernel_timer = None
+        times = timer.summary()
+        bwd_ms = statistics.mean(times["scan_bwd"][N_LAYERS:])       # drop the first step's launches
+        fwd_ms = statistics.mean(times["scan_fwd"][N_LAYERS:])
+        alg = scan_bytes(B * L, 2, 2, True)
+        achieved = alg / (bwd_ms * 1e-3) / 1e9
+        roofline = {
+            "kernel": "scan_bwd_kernel (both directions, one launch per layer)", "bound": "hbm",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "avg_launch_ms": bwd_ms,
+            "algorithmic_bytes_per_launch": alg,
+            "note": "bf16 IO, (7D+4N)*2 B per frame per direction (SURVEY 8d); config-2 tensors fit in the 126 MB L2 and "
+                    "the kernel is FP32-issue/MUFU bound (DESIGN.md), so the HBM fraction is low by construction; "
+                    "scan_fwd avg launch %.4f ms = %.1f GB/s" % (fwd_ms, scan_bytes(B * L, 2, 2, False) / (fwd_ms * 1e-3) / 1e9),
+        }
+        sweep = None if args.no_sweep else scan_sweep(bm, peak)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = run_cpu_baseline(L)
+        line = {
+            "metric": METRIC, "value": frames_total / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": dict(workload_config(args, world), l2="flushed between steps (256 MB write, untimed); per-step CUDA events summed",
+                           launch="CUDA-graph replay" if use_graph else "eager", state="fp32", weights="fp32 master, bf16 autocast"),
+            "clocks": clocks,
+            "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K,
+                    "api": "bimamba_b200.GraphedTrainStep.run(pinned_host_x) -> loss.item()" if use_graph
+                           else "BiMambaBackend.forward_features + backward, eager"},
+            "gpu_launches": launches_per_step * K,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "scan_sweep": sweep,
+            "loss": loss_val,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 1
+#define BIMAMBA_ABI_VERSION 2
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -64,9 +64,12 @@ typedef struct bimamba_scan_desc {
   const float* D;    /* (dim) fp32 or NULL                              */
   const float* delta_bias; /* (dim) fp32 or NULL                        */
   void* out;         /* fwd: (batch, ndir, dim, L) io_dtype              */
-  float* ckpt;       /* (batch, ndir, dim, nchunks, dstate) fp32 state entering each chunk;
+  float* ckpt;       /* (batch, ndir, dim, nchunks, dstate) fp32 state entering each 16-step chunk;
                         written by fwd (may be NULL when nchunks == 1 or no backward is
                         needed), read by bwd when nchunks > 1             */
+  void* ypre;        /* (batch, ndir, dim, L) io_dtype, strides ypre_*: y before the z gate.
+                        Written by fwd when non-NULL; read by bwd to form dz (required there
+                        when z and dz are given)                          */
   /* backward only */
   const void* dout;  /* (batch, ndir, dim, L) io_dtype, strides = out's  */
   void* du;          /* (batch, ndir, dim, L) io_dtype, strides = u's    */
@@ -80,9 +83,9 @@ typedef struct bimamba_scan_desc {
 
   int32_t batch, ndir, dim, seqlen, dstate;
   int32_t io_dtype, bc_dtype, flags;
-  int32_t chunk_items;   /* timesteps per lane (1..8); chunk = 32*chunk_items steps;
-                            nchunks = ceil(seqlen / chunk).  Use bimamba_scan_plan(). */
-  int32_t group_channels;/* channels per CTA (1..32); ngroups = ceil(dim / group_channels) */
+  int32_t chunk_items;   /* steps per chunk = checkpoint interval (16);
+                            nchunks = ceil(seqlen / chunk_items).  Use bimamba_scan_plan(). */
+  int32_t group_channels;/* channels per CTA (even, 2..32); ngroups = ceil(dim / group_channels) */
   int32_t pad_to;        /* if > seqlen: columns [seqlen, pad_to) of every activation output
                             (out; du, ddelta, dz) are written as zeros, so padded rows can be
                             fed to GEMMs that contract over time                */
@@ -94,6 +97,7 @@ typedef struct bimamba_scan_desc {
   int64_t out_bs, out_ds, out_rs;
   int64_t dz_bs, dz_ds, dz_rs;
   int64_t dbc_rs;        /* row stride of dBC_part (>= seqlen); columns [seqlen, dbc_rs) are zeroed */
+  int64_t ypre_bs, ypre_ds, ypre_rs;
 } bimamba_scan_desc;
 
 int bimamba_abi_version(void);

@@ -3,7 +3,9 @@ backend uses).  Import name: this directory is `robust-audio-deepfake-evolution_
 the hyphens import it with `importlib.import_module("robust-audio-deepfake-evolution_b200")` or
 through the top-level alias module `bimamba_b200`."""
 from . import _lib
+from .dist import FlatGradBucket, shard_batch
 from .encoder import BiMambaBackend, PN_BiMambas_Encoder
+from .graph import GraphedForward, GraphedTrainStep
 from .mamba_simple import Mamba
 from .ops import (BiMambaInnerFn, CausalConv1dFn, SelectiveScanFn, bimamba_inner_fn, causal_conv1d_fn,
                   selective_scan_fn)
@@ -11,6 +13,7 @@ from .ops import (BiMambaInnerFn, CausalConv1dFn, SelectiveScanFn, bimamba_inner
 __all__ = [
     "Mamba", "PN_BiMambas_Encoder", "BiMambaBackend", "BiMambaInnerFn", "CausalConv1dFn", "SelectiveScanFn",
     "bimamba_inner_fn", "causal_conv1d_fn", "selective_scan_fn", "install_mamba_ssm_shim",
+    "FlatGradBucket", "shard_batch", "GraphedForward", "GraphedTrainStep",
 ]
 
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libbimamba_sm100.so")
 F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
 FLAG_SILU = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "bimamba_abi_version", "bimamba_last_error", "bimamba_scan_plan",
@@ -27,19 +27,27 @@ class ScanDesc(C.Structure):
     """Mirror of `struct bimamba_scan_desc` (include/bimamba.h)."""
     _fields_ = (
         [(n, C.c_void_p) for n in (
-            "u", "delta", "z", "Bm", "Cm", "A", "D", "delta_bias", "out", "ckpt",
+            "u", "delta", "z", "Bm", "Cm", "A", "D", "delta_bias", "out", "ckpt", "ypre",
             "dout", "du", "ddelta", "dz", "dBC_part", "dA_part", "dD_part", "dbias_part")]
         + [(n, C.c_int32) for n in (
             "batch", "ndir", "dim", "seqlen", "dstate", "io_dtype", "bc_dtype", "flags",
             "chunk_items", "group_channels", "pad_to", "reserved0")]
         + [(n, C.c_int64) for n in (
             "u_bs", "u_ds", "u_rs", "delta_bs", "delta_ds", "delta_rs", "z_bs", "z_ds", "z_rs",
-            "bc_bs", "bc_ds", "bc_rs", "out_bs", "out_ds", "out_rs", "dz_bs", "dz_ds", "dz_rs", "dbc_rs")]
+            "bc_bs", "bc_ds", "bc_rs", "out_bs", "out_ds", "out_rs", "dz_bs", "dz_ds", "dz_rs", "dbc_rs",
+            "ypre_bs", "ypre_ds", "ypre_rs")]
     )
 
 
 _lib = None
 _lock = threading.Lock()
+
+# number of kernels this library has enqueued through the bindings in ops.py (bench.py reports it
+# as `gpu_launches`); every successful entry-point call below enqueues exactly one kernel.
+launch_count = 0
+# optional hook: callable(name) -> context manager, wrapped around each enqueue (bench.py uses it to
+# put CUDA events around individual kernels for the roofline figure)
+kernel_timer = None
 
 
 def load() -> C.CDLL:
@@ -83,9 +91,11 @@ def load() -> C.CDLL:
 
 
 def check(rc: int, what: str) -> None:
+    global launch_count
     if rc != 0:
         msg = load().bimamba_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+    launch_count += 1
 
 
 def scan_plan(seqlen: int, dim: int, rows: int, backward: bool = False):

@@ -6,211 +6,164 @@
 //   out[t] = y[t] * silu(z[t])
 //
 // Mapping (B200-first, not the upstream block-scan):
-//   * operands are channel-first (batch, dir, dim, L): one warp owns one (batch, dir, channel)
-//     row at a time; lane l owns a STRIP of I consecutive scan steps, so a chunk is 32*I steps.
-//   * per state n the lane runs its strip recurrence from zero, the 32 strip summaries
-//     (P = prod a, H = strip-end state) are composed with a 5-step warp-shuffle scan of the
-//     affine maps (P2,H2)o(P1,H1) = (P2 P1, P2 H1 + H2), and the strip is re-run from the
-//     correct incoming state.  The 16 exps per element are computed ONCE and kept in registers
-//     between the two passes - no recompute, no (B,L,D,N) tensor.
-//   * chunk-to-chunk carries live in registers (lane n keeps state n of each of its channels).
-//   * B[t,:], C[t,:] of the chunk are staged once per CTA in shared memory (they are shared by
-//     every channel of the sample); strips are padded to an odd stride so lane-strided reads
-//     are bank-conflict free.
+//   * operands are channel-first (batch, dir, dim, L).  A warp owns TWO channels; lane = 16*c + n
+//     holds state n of channel c in a register for the whole sequence (fp32).
+//   * time is walked in chunks of T = 16 steps.  For each chunk lane n first acts as the owner
+//     of ELEMENT t0+n of its channel: it loads u/delta/z (coalesced), applies softplus / SiLU once
+//     per element, and the 16 lanes broadcast their element to each other by warp shuffle
+//     while the recurrence runs.  The n-sum  y[t] = sum_n C h  is a 16-lane shuffle
+//     reduce-scatter that lands y[t0+j] back on lane j, which gates it and stores it coalesced.
+//     So every transcendental other than the 16 decay exps per element is computed once.
+//   * B[t,n], C[t,n] of a chunk sit in registers of lane n and are reused by all the channels the
+//     warp handles (chunk-outer, channel-inner loop).
 //   * direction 1 walks the same storage back to front (t = L-1-step): flip(M(flip(x))) of
 //     src/models/DualStreamSEMamba.py:476-478 with no flipped copy; both directions are grid.y
 //     of the same launch.
-//   * backward: forward states are recomputed per chunk from the fp32 chunk-boundary
-//     checkpoints written by the forward kernel; dh runs as the mirrored (shfl_down) scan with
-//     the same a[] registers; dB/dC are reduced over the CTA's channels in shared memory and
-//     written as per-group partials; dA/dD/dbias as per-(batch,dir,channel) partials.  The
-//     cross-CTA sums are done in fixed order by bimamba_reduce_partials.
+//   * training forward also writes the fp32 state entering every chunk ("checkpoints") and the
+//     pre-gate y.  Backward walks the chunks last to first: it re-runs the 16 steps of a chunk
+//     from its checkpoint keeping a[t], h[t] in registers, then runs the reverse recurrence for
+//     dh over the same registers - no (B, L, D, N) tensor, 16 exps per element in each pass.
+//     dB/dC accumulate in registers over the warp's channels, are combined over the CTA's warps
+//     in fixed order through shared memory and written as per-group partials; dA/dD/dbias are
+//     per-(batch, dir, channel) partials.  All cross-CTA sums are done in fixed order by
+//     bimamba_reduce_partials: the whole backward is deterministic (no atomics).
 #include "common.cuh"
 
 namespace bimamba {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-constexpr int kMaxCpw = 4;  // channels per warp (group_channels <= kMaxCpw * kWarps)
-constexpr int kN = 16;      // d_state handled by these kernels
+constexpr int kT = 16;       // steps per chunk == checkpoint interval
+constexpr int kN = 16;       // d_state handled by these kernels
+constexpr int kMaxG = 32;    // channels per CTA
+constexpr int kMaxKP = kMaxG / (2 * kWarps);  // channel pairs per warp
 
-template <int I>
-struct Geo {
-  static constexpr int IS = I | 1;     // odd strip stride in shared memory
-  static constexpr int ROW = 32 * IS;  // floats per staged row
-  static constexpr int TC = 32 * I;    // scan steps per chunk
-};
-
-// position of chunk-local step tau in a staged row
-template <int I>
-__device__ __forceinline__ int spos(int tau) {
-  return (tau / I) * Geo<I>::IS + (tau % I);
-}
-
-template <int I>
-__device__ __forceinline__ void stage_bc(float* __restrict__ sB, float* __restrict__ sC,
-                                         const bimamba_scan_desc& p, int b, int dir, int chunk) {
-  constexpr int TC = Geo<I>::TC, ROW = Geo<I>::ROW;
-  const int L = p.seqlen;
-  const int64_t base = (int64_t)b * p.bc_bs + (int64_t)dir * p.bc_ds;
-  for (int idx = threadIdx.x; idx < 2 * kN * TC; idx += kThreads) {
-    const int row = idx / TC;
-    const int tau = idx - row * TC;
-    const int tg = chunk * TC + tau;
-    const int n = row & (kN - 1);
-    float v = 0.f;
-    if (tg < L) {
-      const int t = dir ? (L - 1 - tg) : tg;
-      v = ld_f(row < kN ? p.Bm : p.Cm, base + (int64_t)n * p.bc_rs + t, p.bc_dtype);
-    }
-    (row < kN ? sB : sC)[n * ROW + spos<I>(tau)] = v;
-  }
-}
-
-// inclusive scan over lanes of the affine maps (P, H), composing left-to-right (lower lanes first)
-__device__ __forceinline__ void warp_scan_up(float& P, float& H, int lane) {
+// Sum over the 16 lanes of a half-warp of v[0..15]; lane j (within its half) returns sum of v[j].
+// Fixed tree -> deterministic.
+__device__ __forceinline__ float reduce_scatter16(float (&v)[16], int r) {
+  const bool b3 = r & 8, b2 = r & 4, b1 = r & 2, b0 = r & 1;
+  float w8[8];
 #pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const float Pp = __shfl_up_sync(kFull, P, off);
-    const float Hp = __shfl_up_sync(kFull, H, off);
-    if (lane >= off) {
-      H = fmaf(P, Hp, H);
-      P *= Pp;
-    }
+  for (int i = 0; i < 8; ++i) {
+    const float send = b3 ? v[i] : v[i + 8];
+    const float keep = b3 ? v[i + 8] : v[i];
+    w8[i] = keep + __shfl_xor_sync(kFull, send, 8);
   }
-}
-// mirrored: composes right-to-left (higher lanes first)
-__device__ __forceinline__ void warp_scan_down(float& P, float& H, int lane) {
+  float w4[4];
 #pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const float Pp = __shfl_down_sync(kFull, P, off);
-    const float Hp = __shfl_down_sync(kFull, H, off);
-    if (lane + off < 32) {
-      H = fmaf(P, Hp, H);
-      P *= Pp;
-    }
+  for (int i = 0; i < 4; ++i) {
+    const float send = b2 ? w8[i] : w8[i + 4];
+    const float keep = b2 ? w8[i + 4] : w8[i];
+    w4[i] = keep + __shfl_xor_sync(kFull, send, 4);
   }
+  float w2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b1 ? w4[i] : w4[i + 2];
+    const float keep = b1 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(kFull, send, 2);
+  }
+  const float send = b0 ? w2[0] : w2[1];
+  const float keep = b0 ? w2[1] : w2[0];
+  return keep + __shfl_xor_sync(kFull, send, 1);
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+__device__ __forceinline__ float half_sum(float v) {  // all-reduce over the 16 lanes of a half-warp
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+  for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
   return v;
 }
 
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-template <int I, bool MULTI>
 __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const bimamba_scan_desc p) {
-  constexpr int IS = Geo<I>::IS, ROW = Geo<I>::ROW, TC = Geo<I>::TC;
-  extern __shared__ float smem[];
-  float* sB = smem;
-  float* sC = sB + kN * ROW;
-  float* sA = sC + kN * ROW;  // [group_channels][16], A * log2(e)
-
   const int b = blockIdx.z, dir = blockIdx.y, G = p.group_channels, d0 = blockIdx.x * G;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, n = lane & 15;
   const int L = p.seqlen, dt = p.io_dtype;
-  const int nchunks = MULTI ? (L + TC - 1) / TC : 1;
-  const int gch = min(G, p.dim - d0);
+  const int nck = (L + kT - 1) / kT;
   const bool softplus = (p.flags & BIMAMBA_FLAG_SOFTPLUS) != 0;
+  const int64_t bd = (int64_t)b * p.ndir + dir;
+  const int64_t bcb = (int64_t)b * p.bc_bs + (int64_t)dir * p.bc_ds + (int64_t)n * p.bc_rs;
 
-  for (int idx = threadIdx.x; idx < gch * kN; idx += kThreads) sA[idx] = p.A[(int64_t)d0 * kN + idx] * kLog2e;
-
-  float carry[kMaxCpw];
+  float h[kMaxKP], A2[kMaxKP], bias[kMaxKP], Dd[kMaxKP];
+  int ch[kMaxKP];
 #pragma unroll
-  for (int k = 0; k < kMaxCpw; ++k) carry[k] = 0.f;
+  for (int k = 0; k < kMaxKP; ++k) {
+    const int cl = 2 * (warp + kWarps * k) + half;
+    const int c = d0 + cl;
+    const bool ok = cl < G && c < p.dim;
+    ch[k] = ok ? c : -1;
+    h[k] = 0.f;
+    A2[k] = ok ? __ldg(p.A + (int64_t)c * kN + n) * kLog2e : 0.f;
+    bias[k] = (ok && p.delta_bias) ? __ldg(p.delta_bias + c) : 0.f;
+    Dd[k] = (ok && p.D) ? __ldg(p.D + c) : 0.f;
+  }
 
-  for (int c = 0; c < nchunks; ++c) {
-    __syncthreads();
-    stage_bc<I>(sB, sC, p, b, dir, c);
-    __syncthreads();
-
+  for (int c0 = 0; c0 < nck; ++c0) {
+    const int tau0 = c0 * kT;
+    float Bv[kT], Cv[kT];
 #pragma unroll
-    for (int k = 0; k < kMaxCpw; ++k) {
-      const int cl = warp + k * kWarps;
-      if (cl < gch) {
-        const int d = d0 + cl;
-        const int64_t ub = (int64_t)b * p.u_bs + (int64_t)dir * p.u_ds + (int64_t)d * p.u_rs;
-        const int64_t db = (int64_t)b * p.delta_bs + (int64_t)dir * p.delta_ds + (int64_t)d * p.delta_rs;
-        const int64_t zb = (int64_t)b * p.z_bs + (int64_t)dir * p.z_ds + (int64_t)d * p.z_rs;
-        const int64_t ob = (int64_t)b * p.out_bs + (int64_t)dir * p.out_ds + (int64_t)d * p.out_rs;
-        const float bias = p.delta_bias ? __ldg(p.delta_bias + d) : 0.f;
-        const float Dd = p.D ? __ldg(p.D + d) : 0.f;
-
-        if (MULTI && p.ckpt && lane < kN)
-          p.ckpt[((((int64_t)b * p.ndir + dir) * p.dim + d) * nchunks + c) * kN + lane] = carry[k];
-        if (c == 0)
-          for (int t = L + lane; t < p.pad_to; t += 32) st_f(p.out, ob + t, 0.f, dt);
-
-        float dl[I], dlu[I], y[I], zv[I];
-        float sumd = 0.f;
-        const int tg0 = c * TC + lane * I;
-#pragma unroll
-        for (int i = 0; i < I; ++i) {
-          const int tg = tg0 + i;
-          float uv = 0.f, dv = 0.f;
-          zv[i] = 0.f;
-          if (tg < L) {
-            const int t = dir ? (L - 1 - tg) : tg;
-            uv = ld_f(p.u, ub + t, dt);
-            dv = ld_f(p.delta, db + t, dt) + bias;
-            if (softplus) dv = softplus_f(dv);
-            if (p.z) zv[i] = ld_f(p.z, zb + t, dt);
-          }
-          dl[i] = dv;
-          dlu[i] = dv * uv;
-          y[i] = Dd * uv;
-          sumd += dv;
-        }
-
-        const float* sAd = sA + cl * kN;
-        const float* sBl = sB + lane * IS;
-        const float* sCl = sC + lane * IS;
-#pragma unroll 2
-        for (int n = 0; n < kN; ++n) {
-          const float A2 = sAd[n];
-          float a[I], bb[I];
-          float H = 0.f;
-#pragma unroll
-          for (int i = 0; i < I; ++i) {
-            a[i] = ex2_approx(dl[i] * A2);
-            bb[i] = dlu[i] * sBl[n * ROW + i];
-            H = fmaf(a[i], H, bb[i]);
-          }
-          float P = ex2_approx(sumd * A2);
-          warp_scan_up(P, H, lane);
-          float Hin = __shfl_up_sync(kFull, H, 1);
-          float Pin = __shfl_up_sync(kFull, P, 1);
-          if (lane == 0) {
-            Hin = 0.f;
-            Pin = 1.f;
-          }
-          float h = Hin;
-          if (MULTI) {
-            const float cin = __shfl_sync(kFull, carry[k], n);
-            h = fmaf(Pin, cin, Hin);
-            const float P31 = __shfl_sync(kFull, P, 31);
-            const float H31 = __shfl_sync(kFull, H, 31);
-            if (lane == n) carry[k] = fmaf(P31, cin, H31);
-          }
-#pragma unroll
-          for (int i = 0; i < I; ++i) {
-            h = fmaf(a[i], h, bb[i]);
-            y[i] = fmaf(sCl[n * ROW + i], h, y[i]);
-          }
-        }
+    for (int i = 0; i < kT; ++i) {
+      const int tau = tau0 + i;
+      Bv[i] = 0.f;
+      Cv[i] = 0.f;
+      if (tau < L) {
+        const int t = dir ? (L - 1 - tau) : tau;
+        Bv[i] = ld_f(p.Bm, bcb + t, p.bc_dtype);
+        Cv[i] = ld_f(p.Cm, bcb + t, p.bc_dtype);
+      }
+    }
+    const int tauj = tau0 + n;  // the element this lane owns in this chunk
+    const int tj = dir ? (L - 1 - tauj) : tauj;
 
 #pragma unroll
-        for (int i = 0; i < I; ++i) {
-          const int tg = tg0 + i;
-          if (tg < L) {
-            const int t = dir ? (L - 1 - tg) : tg;
-            float o = y[i];
-            if (p.z) o *= zv[i] * sigmoid_f(zv[i]);
-            st_f(p.out, ob + t, o, dt);
-          }
+    for (int k = 0; k < kMaxKP; ++k) {
+      // warp-uniform skip: the pair index is out of range for the whole warp
+      if (2 * (warp + kWarps * k) >= G || d0 + 2 * (warp + kWarps * k) >= p.dim) continue;
+      const int c = ch[k];
+      const bool ok = c >= 0;
+      const int cc = ok ? c : 0;
+      const int64_t ub = (int64_t)b * p.u_bs + (int64_t)dir * p.u_ds + (int64_t)cc * p.u_rs;
+      const int64_t db = (int64_t)b * p.delta_bs + (int64_t)dir * p.delta_ds + (int64_t)cc * p.delta_rs;
+      const int64_t zb = (int64_t)b * p.z_bs + (int64_t)dir * p.z_ds + (int64_t)cc * p.z_rs;
+      const int64_t ob = (int64_t)b * p.out_bs + (int64_t)dir * p.out_ds + (int64_t)cc * p.out_rs;
+
+      if (p.ckpt && ok) p.ckpt[((bd * p.dim + c) * nck + c0) * kN + n] = h[k];
+
+      const bool live = ok && tauj < L;
+      float uj = 0.f, dj = 0.f, zj = 0.f;
+      if (live) {
+        uj = ld_f(p.u, ub + tj, dt);
+        dj = ld_f(p.delta, db + tj, dt) + bias[k];
+        if (softplus) dj = softplus_f(dj);
+        if (p.z) zj = ld_f(p.z, zb + tj, dt);
+      }
+      const float duj = dj * uj;
+
+      float pr[kT];
+      float hk = h[k];
+      const float a2 = A2[k];
+#pragma unroll
+      for (int i = 0; i < kT; ++i) {
+        const float di = __shfl_sync(kFull, dj, i, 16);
+        const float dui = __shfl_sync(kFull, duj, i, 16);
+        const float a = ex2_approx(di * a2);
+        hk = fmaf(a, hk, dui * Bv[i]);
+        pr[i] = Cv[i] * hk;
+      }
+      h[k] = hk;
+      float y = reduce_scatter16(pr, n);
+      y = fmaf(Dd[k], uj, y);
+      if (live) {
+        if (p.ypre) st_f(p.ypre, ob + tj, y, dt);
+        if (p.z) y *= zj * sigmoid_f(zj);
+        st_f(p.out, ob + tj, y, dt);
+      }
+      if (c0 == 0 && ok) {
+        for (int t = L + n; t < p.pad_to; t += 16) {
+          st_f(p.out, ob + t, 0.f, dt);
+          if (p.ypre) st_f(p.ypre, ob + t, 0.f, dt);
         }
       }
     }
@@ -220,29 +173,25 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const bimamba_scan_d
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-template <int I, bool MULTI>
 __global__ void __launch_bounds__(kThreads) scan_bwd_kernel(const bimamba_scan_desc p) {
-  constexpr int IS = Geo<I>::IS, ROW = Geo<I>::ROW, TC = Geo<I>::TC;
-  extern __shared__ float smem[];
-  float* sB = smem;
-  float* sC = sB + kN * ROW;
-  float* sdB = sC + kN * ROW;
-  float* sdC = sdB + kN * ROW;
-  float* sA = sdC + kN * ROW;              // [G][16]
-  float* sRed = sA + p.group_channels * kN;  // [kWarps][16][33]
+  __shared__ float sCarry[kMaxG * kN];             // m = a*dh flowing to earlier steps, per (channel, n)
+  __shared__ float sdA[kMaxG * kN];
+  __shared__ float sRed[kWarps * 2 * kT * kN];     // per-warp dB/dC chunk tiles
 
   const int b = blockIdx.z, dir = blockIdx.y, G = p.group_channels, g = blockIdx.x, d0 = g * G;
   const int ngroups = gridDim.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, n = lane & 15;
   const int L = p.seqlen, dt = p.io_dtype;
-  const int nchunks = MULTI ? (L + TC - 1) / TC : 1;
-  const int gch = min(G, p.dim - d0);
+  const int nck = (L + kT - 1) / kT;
   const bool softplus = (p.flags & BIMAMBA_FLAG_SOFTPLUS) != 0;
+  const bool gated = p.z != nullptr;
   const int64_t bd = (int64_t)b * p.ndir + dir;
-  float* myRed = sRed + warp * (kN * 33);
+  const int64_t bcb = (int64_t)b * p.bc_bs + (int64_t)dir * p.bc_ds + (int64_t)n * p.bc_rs;
 
-  for (int idx = threadIdx.x; idx < gch * kN; idx += kThreads) sA[idx] = p.A[(int64_t)d0 * kN + idx] * kLog2e;
-
+  for (int i = threadIdx.x; i < kMaxG * kN; i += kThreads) {
+    sCarry[i] = 0.f;
+    sdA[i] = 0.f;
+  }
   float* partB = p.dBC_part + ((bd * ngroups + g) * 2) * (int64_t)kN * p.dbc_rs;
   {  // zero the padding columns so the ordered reduction can run over whole rows
     const int padw = (int)(p.dbc_rs - L);
@@ -250,196 +199,168 @@ __global__ void __launch_bounds__(kThreads) scan_bwd_kernel(const bimamba_scan_d
       partB[(int64_t)(idx / padw) * p.dbc_rs + L + (idx % padw)] = 0.f;
   }
 
-  float carryR[kMaxCpw], dAacc[kMaxCpw], dDacc[kMaxCpw], dbacc[kMaxCpw];
+  float A2[kMaxKP], bias[kMaxKP], Dd[kMaxKP], dDacc[kMaxKP], dbacc[kMaxKP];
+  int ch[kMaxKP];
 #pragma unroll
-  for (int k = 0; k < kMaxCpw; ++k) carryR[k] = dAacc[k] = dDacc[k] = dbacc[k] = 0.f;
+  for (int k = 0; k < kMaxKP; ++k) {
+    const int cl = 2 * (warp + kWarps * k) + half;
+    const int c = d0 + cl;
+    const bool ok = cl < G && c < p.dim;
+    ch[k] = ok ? c : -1;
+    A2[k] = ok ? __ldg(p.A + (int64_t)c * kN + n) * kLog2e : 0.f;
+    bias[k] = (ok && p.delta_bias) ? __ldg(p.delta_bias + c) : 0.f;
+    Dd[k] = (ok && p.D) ? __ldg(p.D + c) : 0.f;
+    dDacc[k] = 0.f;
+    dbacc[k] = 0.f;
+  }
+  __syncthreads();
 
-  for (int c = nchunks - 1; c >= 0; --c) {
-    __syncthreads();
-    stage_bc<I>(sB, sC, p, b, dir, c);
-    for (int idx = threadIdx.x; idx < 2 * kN * ROW; idx += kThreads) sdB[idx] = 0.f;  // sdB and sdC are adjacent
-    __syncthreads();
+  for (int c0 = nck - 1; c0 >= 0; --c0) {
+    const int tau0 = c0 * kT;
+    float Bv[kT], Cv[kT], dBa[kT], dCa[kT];
+#pragma unroll
+    for (int i = 0; i < kT; ++i) {
+      const int tau = tau0 + i;
+      Bv[i] = 0.f;
+      Cv[i] = 0.f;
+      dBa[i] = 0.f;
+      dCa[i] = 0.f;
+      if (tau < L) {
+        const int t = dir ? (L - 1 - tau) : tau;
+        Bv[i] = ld_f(p.Bm, bcb + t, p.bc_dtype);
+        Cv[i] = ld_f(p.Cm, bcb + t, p.bc_dtype);
+      }
+    }
+    const int tauj = tau0 + n;
+    const int tj = dir ? (L - 1 - tauj) : tauj;
 
 #pragma unroll
-    for (int k = 0; k < kMaxCpw; ++k) {
-      const int cl = warp + k * kWarps;
-      if (cl < gch) {
-        const int d = d0 + cl;
-        const int64_t ub = (int64_t)b * p.u_bs + (int64_t)dir * p.u_ds + (int64_t)d * p.u_rs;
-        const int64_t db = (int64_t)b * p.delta_bs + (int64_t)dir * p.delta_ds + (int64_t)d * p.delta_rs;
-        const int64_t zb = (int64_t)b * p.z_bs + (int64_t)dir * p.z_ds + (int64_t)d * p.z_rs;
-        const int64_t ob = (int64_t)b * p.out_bs + (int64_t)dir * p.out_ds + (int64_t)d * p.out_rs;
-        const int64_t dzb = (int64_t)b * p.dz_bs + (int64_t)dir * p.dz_ds + (int64_t)d * p.dz_rs;
-        const float bias = p.delta_bias ? __ldg(p.delta_bias + d) : 0.f;
-        const float Dd = p.D ? __ldg(p.D + d) : 0.f;
+    for (int k = 0; k < kMaxKP; ++k) {
+      if (2 * (warp + kWarps * k) >= G || d0 + 2 * (warp + kWarps * k) >= p.dim) continue;
+      const int c = ch[k];
+      const bool ok = c >= 0;
+      const int cc = ok ? c : 0;
+      const int cl = 2 * (warp + kWarps * k) + half;
+      const int64_t ub = (int64_t)b * p.u_bs + (int64_t)dir * p.u_ds + (int64_t)cc * p.u_rs;
+      const int64_t db = (int64_t)b * p.delta_bs + (int64_t)dir * p.delta_ds + (int64_t)cc * p.delta_rs;
+      const int64_t zb = (int64_t)b * p.z_bs + (int64_t)dir * p.z_ds + (int64_t)cc * p.z_rs;
+      const int64_t ob = (int64_t)b * p.out_bs + (int64_t)dir * p.out_ds + (int64_t)cc * p.out_rs;
+      const int64_t dzb = (int64_t)b * p.dz_bs + (int64_t)dir * p.dz_ds + (int64_t)cc * p.dz_rs;
+      const int64_t yb = (int64_t)b * p.ypre_bs + (int64_t)dir * p.ypre_ds + (int64_t)cc * p.ypre_rs;
 
-        if (c == 0) {
-          for (int t = L + lane; t < p.pad_to; t += 32) {
-            st_f(p.du, ub + t, 0.f, dt);
-            st_f(p.ddelta, db + t, 0.f, dt);
-            if (p.z && p.dz) st_f(p.dz, dzb + t, 0.f, dt);
-          }
+      const bool live = ok && tauj < L;
+      float uj = 0.f, dj = 0.f, zj = 0.f, doj = 0.f, sgj = 0.f, gj = 0.f;
+      if (live) {
+        uj = ld_f(p.u, ub + tj, dt);
+        dj = ld_f(p.delta, db + tj, dt) + bias[k];
+        if (softplus) dj = softplus_f(dj);
+        doj = ld_f(p.dout, ob + tj, dt);
+        gj = doj;
+        if (gated) {
+          zj = ld_f(p.z, zb + tj, dt);
+          sgj = sigmoid_f(zj);
+          gj = doj * zj * sgj;
         }
-        float cfw = 0.f;  // lane n: forward state n entering this chunk
-        if (MULTI && c > 0 && lane < kN) cfw = p.ckpt[(((bd * p.dim + d) * nchunks) + c) * kN + lane];
+      }
+      const float duj = dj * uj;
+      const float hstart = (ok && c0 > 0) ? p.ckpt[((bd * p.dim + c) * nck + c0) * kN + n] : 0.f;
 
-        float uu[I], dl[I], dlu[I], gg[I], y[I], zv[I], dov[I], ddA[I], ddu[I];
-        float sumd = 0.f;
-        const int tg0 = c * TC + lane * I;
+      // ---- re-run the chunk forward, keeping a[t], h[t] ----
+      float a[kT], hh[kT];
+      const float a2 = A2[k];
+      {
+        float hk = hstart;
 #pragma unroll
-        for (int i = 0; i < I; ++i) {
-          const int tg = tg0 + i;
-          float uv = 0.f, dv = 0.f, zz = 0.f, dy = 0.f;
-          if (tg < L) {
-            const int t = dir ? (L - 1 - tg) : tg;
-            uv = ld_f(p.u, ub + t, dt);
-            dv = ld_f(p.delta, db + t, dt) + bias;
-            if (softplus) dv = softplus_f(dv);
-            dy = ld_f(p.dout, ob + t, dt);
-            if (p.z) zz = ld_f(p.z, zb + t, dt);
-          }
-          uu[i] = uv;
-          dl[i] = dv;
-          dlu[i] = dv * uv;
-          zv[i] = zz;
-          dov[i] = dy;
-          gg[i] = p.z ? dy * zz * sigmoid_f(zz) : dy;
-          y[i] = Dd * uv;
-          ddA[i] = 0.f;
-          ddu[i] = 0.f;
-          sumd += dv;
+        for (int i = 0; i < kT; ++i) {
+          const float di = __shfl_sync(kFull, dj, i, 16);
+          const float dui = __shfl_sync(kFull, duj, i, 16);
+          a[i] = ex2_approx(di * a2);
+          hk = fmaf(a[i], hk, dui * Bv[i]);
+          hh[i] = hk;
         }
+      }
+      // ---- reverse recurrence:  dh_i = g_i C_i + m_{i+1},  m_i = a_i dh_i ----
+      float m = sCarry[cl * kN + n];
+      float dAl = 0.f;
+#pragma unroll
+      for (int i = kT - 1; i >= 0; --i) {
+        const float gi = __shfl_sync(kFull, gj, i, 16);
+        const float di = __shfl_sync(kFull, dj, i, 16);
+        const float dui = __shfl_sync(kFull, duj, i, 16);
+        const float dh = fmaf(gi, Cv[i], m);
+        m = a[i] * dh;
+        const float hp = (i == 0) ? hstart : hh[i - 1];
+        const float daa = m * hp;
+        dAl = fmaf(daa, di, dAl);
+        dBa[i] = fmaf(dh, dui, dBa[i]);
+        dCa[i] = fmaf(gi, hh[i], dCa[i]);
+        a[i] = daa * a2;       // a[i] is dead: reuse as the d(delta) partial (x ln2 later)
+        hh[i] = dh * Bv[i];    // hh[i] is dead for the remaining steps: reuse as the d(delta*u) partial
+      }
+      sCarry[cl * kN + n] = m;
+      sdA[cl * kN + n] += dAl;
+      const float rA = reduce_scatter16(a, n);
+      const float rU = reduce_scatter16(hh, n);
 
-        const float* sAd = sA + cl * kN;
-        const int so = lane * IS;
-#pragma unroll 1
-        for (int n = 0; n < kN; ++n) {
-          const float A2 = sAd[n];
-          const float* sBn = sB + n * ROW + so;
-          const float* sCn = sC + n * ROW + so;
-          float a[I], h[I], Bv[I], Cv[I];
-          float H = 0.f;
-#pragma unroll
-          for (int i = 0; i < I; ++i) {
-            Bv[i] = sBn[i];
-            Cv[i] = sCn[i];
-            a[i] = ex2_approx(dl[i] * A2);
-            h[i] = dlu[i] * Bv[i];  // holds b[i] until pass 2
-            H = fmaf(a[i], H, h[i]);
-          }
-          const float Pstrip = ex2_approx(sumd * A2);
-          float P = Pstrip;
-          warp_scan_up(P, H, lane);
-          float Hin = __shfl_up_sync(kFull, H, 1);
-          float Pin = __shfl_up_sync(kFull, P, 1);
-          if (lane == 0) {
-            Hin = 0.f;
-            Pin = 1.f;
-          }
-          float hin = Hin;
-          if (MULTI) {
-            const float cin = __shfl_sync(kFull, cfw, n);
-            hin = fmaf(Pin, cin, Hin);
-          }
-          {
-            float hh = hin;
-#pragma unroll
-            for (int i = 0; i < I; ++i) {
-              hh = fmaf(a[i], hh, h[i]);
-              h[i] = hh;
-              y[i] = fmaf(Cv[i], hh, y[i]);
-            }
-          }
-          // ---- reverse: m_i = a_i * dh_i, dh_i = g_i C_i + m_{i+1} ----
-          float M = 0.f;
-#pragma unroll
-          for (int i = I - 1; i >= 0; --i) M = a[i] * fmaf(gg[i], Cv[i], M);
-          float Q = Pstrip;
-          warp_scan_down(Q, M, lane);
-          float Min = __shfl_down_sync(kFull, M, 1);
-          float Qin = __shfl_down_sync(kFull, Q, 1);
-          if (lane == 31) {
-            Min = 0.f;
-            Qin = 1.f;
-          }
-          float m = Min;
-          if (MULTI) {
-            const float rin = __shfl_sync(kFull, carryR[k], n);
-            m = fmaf(Qin, rin, Min);
-            const float Q0 = __shfl_sync(kFull, Q, 0);
-            const float M0 = __shfl_sync(kFull, M, 0);
-            if (lane == n) carryR[k] = fmaf(Q0, rin, M0);
-          }
-          float dAl = 0.f;
-#pragma unroll
-          for (int i = I - 1; i >= 0; --i) {
-            const float dh = fmaf(gg[i], Cv[i], m);
-            m = a[i] * dh;
-            const float hp = (i == 0) ? hin : h[i - 1];
-            const float daa = m * hp;
-            dAl = fmaf(daa, dl[i], dAl);
-            ddA[i] = fmaf(daa, A2, ddA[i]);
-            ddu[i] = fmaf(dh, Bv[i], ddu[i]);
-            atomicAdd(sdB + n * ROW + so + i, dh * dlu[i]);
-            atomicAdd(sdC + n * ROW + so + i, gg[i] * h[i]);
-          }
-          myRed[n * 33 + lane] = dAl;
+      if (live) {
+        dDacc[k] = fmaf(gj, uj, dDacc[k]);
+        const float duv = fmaf(gj, Dd[k], dj * rU);
+        float ddl = fmaf(uj, rU, rA * kLn2);
+        if (softplus) ddl *= (1.f - expf(-dj));  // sigmoid(raw) == 1 - exp(-softplus(raw))
+        dbacc[k] += ddl;
+        st_f(p.du, ub + tj, duv, dt);
+        st_f(p.ddelta, db + tj, ddl, dt);
+        if (gated && p.dz) {
+          const float yj = ld_f(p.ypre, yb + tj, dt);
+          st_f(p.dz, dzb + tj, doj * yj * sgj * (1.f + zj * (1.f - sgj)), dt);
         }
-        __syncwarp();
-        if (lane < kN) {
-          float s = 0.f;
-#pragma unroll 8
-          for (int j = 0; j < 32; ++j) s += myRed[lane * 33 + j];
-          dAacc[k] += s;
+      }
+      if (c0 == 0 && ok) {
+        for (int t = L + n; t < p.pad_to; t += 16) {
+          st_f(p.du, ub + t, 0.f, dt);
+          st_f(p.ddelta, db + t, 0.f, dt);
+          if (gated && p.dz) st_f(p.dz, dzb + t, 0.f, dt);
         }
-        __syncwarp();
-
-        float dDl = 0.f, dbl = 0.f;
-#pragma unroll
-        for (int i = 0; i < I; ++i) {
-          const int tg = tg0 + i;
-          if (tg < L) {
-            const int t = dir ? (L - 1 - tg) : tg;
-            dDl = fmaf(gg[i], uu[i], dDl);
-            const float duv = fmaf(gg[i], Dd, dl[i] * ddu[i]);
-            float ddl = fmaf(uu[i], ddu[i], ddA[i] * kLn2);
-            if (softplus) ddl *= (1.f - expf(-dl[i]));  // sigmoid(raw) == 1 - exp(-softplus(raw))
-            dbl += ddl;
-            st_f(p.du, ub + t, duv, dt);
-            st_f(p.ddelta, db + t, ddl, dt);
-            if (p.z && p.dz) {
-              const float sg = sigmoid_f(zv[i]);
-              st_f(p.dz, dzb + t, dov[i] * y[i] * sg * (1.f + zv[i] * (1.f - sg)), dt);
-            }
-          }
-        }
-        dDacc[k] += warp_sum(dDl);
-        dbacc[k] += warp_sum(dbl);
       }
     }
 
-    __syncthreads();
-    // write this chunk's dB / dC partial tile (natural time order)
-    for (int idx = threadIdx.x; idx < 2 * kN * TC; idx += kThreads) {
-      const int row = idx / TC;
-      const int tau = idx - row * TC;
-      const int tg = c * TC + tau;
-      if (tg < L) {
-        const int t = dir ? (L - 1 - tg) : tg;
-        partB[(int64_t)row * p.dbc_rs + t] = sdB[row * ROW + spos<I>(tau)];
+    // ---- combine dB/dC of this chunk: halves by shuffle, warps through shared memory (fixed order) ----
+    float* myRed = sRed + warp * (2 * kT * kN);
+#pragma unroll
+    for (int i = 0; i < kT; ++i) {
+      const float vb = dBa[i] + __shfl_xor_sync(kFull, dBa[i], 16);
+      const float vc = dCa[i] + __shfl_xor_sync(kFull, dCa[i], 16);
+      if (half == 0) {
+        myRed[n * kT + i] = vb;  // [row n][step i]
+        myRed[kT * kN + n * kT + i] = vc;
       }
     }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * kN * kT; idx += kThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += sRed[w * (2 * kT * kN) + idx];
+      const int row = idx / kT;  // 0..15 dB rows, 16..31 dC rows
+      const int tau = tau0 + (idx % kT);
+      if (tau < L) {
+        const int t = dir ? (L - 1 - tau) : tau;
+        partB[(int64_t)row * p.dbc_rs + t] = s;
+      }
+    }
+    __syncthreads();
   }
 
 #pragma unroll
-  for (int k = 0; k < kMaxCpw; ++k) {
-    const int cl = warp + k * kWarps;
-    if (cl < gch) {
-      const int d = d0 + cl;
-      if (lane < kN) p.dA_part[(bd * p.dim + d) * kN + lane] = dAacc[k];
-      if (lane == 0) {
-        if (p.dD_part) p.dD_part[bd * p.dim + d] = dDacc[k];
-        if (p.dbias_part) p.dbias_part[bd * p.dim + d] = dbacc[k];
+  for (int k = 0; k < kMaxKP; ++k) {
+    const float sD = half_sum(dDacc[k]);
+    const float sb = half_sum(dbacc[k]);
+    const int c = ch[k];
+    if (c >= 0) {
+      const int cl = 2 * (warp + kWarps * k) + half;
+      p.dA_part[(bd * p.dim + c) * kN + n] = sdA[cl * kN + n];
+      if (n == 0) {
+        if (p.dD_part) p.dD_part[bd * p.dim + c] = sD;
+        if (p.dbias_part) p.dbias_part[bd * p.dim + c] = sb;
       }
     }
   }
@@ -455,73 +376,24 @@ void set_err(const char* msg) {
   g_err[i] = 0;
 }
 
-template <int I>
-size_t fwd_smem(int G) { return sizeof(float) * (2 * kN * Geo<I>::ROW + G * kN); }
-template <int I>
-size_t bwd_smem(int G) { return sizeof(float) * (4 * kN * Geo<I>::ROW + G * kN + kWarps * kN * 33); }
-
-template <int I, bool MULTI>
-int launch_fwd(const bimamba_scan_desc& d, cudaStream_t st) {
-  const size_t smem = fwd_smem<I>(d.group_channels);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(scan_fwd_kernel<I, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
-  }
-  dim3 grid((d.dim + d.group_channels - 1) / d.group_channels, d.ndir, d.batch);
-  scan_fwd_kernel<I, MULTI><<<grid, kThreads, smem, st>>>(d);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
-  return 0;
-}
-
-template <int I, bool MULTI>
-int launch_bwd(const bimamba_scan_desc& d, cudaStream_t st) {
-  const size_t smem = bwd_smem<I>(d.group_channels);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(scan_bwd_kernel<I, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
-  }
-  dim3 grid((d.dim + d.group_channels - 1) / d.group_channels, d.ndir, d.batch);
-  scan_bwd_kernel<I, MULTI><<<grid, kThreads, smem, st>>>(d);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
-  return 0;
-}
-
 int check_desc(const bimamba_scan_desc* d, bool bwd) {
   if (!d) { set_err("null descriptor"); return -1; }
   if (d->dstate != kN) { set_err("dstate must be 16"); return -2; }
   if (d->batch < 0 || d->ndir < 1 || d->ndir > 2 || d->dim < 1 || d->seqlen < 0) { set_err("bad sizes"); return -3; }
   if (d->batch > 65535) { set_err("batch > 65535 not supported by this launch geometry"); return -3; }
-  if (d->chunk_items < 1 || d->chunk_items > 8) { set_err("chunk_items must be 1..8"); return -4; }
-  if (d->group_channels < 1 || d->group_channels > kMaxCpw * kWarps) { set_err("group_channels must be 1..32"); return -5; }
+  if (d->chunk_items != kT) { set_err("chunk_items must be 16 (use bimamba_scan_plan)"); return -4; }
+  if (d->group_channels < 2 || d->group_channels > kMaxG || (d->group_channels & 1)) { set_err("group_channels must be even, 2..32"); return -5; }
   if (d->io_dtype < 0 || d->io_dtype > 2 || d->bc_dtype < 0 || d->bc_dtype > 2) { set_err("bad dtype"); return -6; }
   if (!d->u || !d->delta || !d->A || !d->Bm || !d->Cm) { set_err("null operand"); return -7; }
   if (!bwd && !d->out) { set_err("null out"); return -7; }
-  const int nchunks = (d->seqlen + 32 * d->chunk_items - 1) / (32 * d->chunk_items);
   if (bwd) {
     if (!d->dout || !d->du || !d->ddelta || !d->dBC_part || !d->dA_part) { set_err("null backward operand"); return -8; }
-    if (nchunks > 1 && !d->ckpt) { set_err("backward over several chunks needs the forward checkpoints"); return -9; }
+    if (d->seqlen > kT && !d->ckpt) { set_err("backward needs the forward checkpoints"); return -9; }
     if (d->dbc_rs < d->seqlen) { set_err("dbc_rs < seqlen"); return -10; }
+    if (d->z && d->dz && !d->ypre) { set_err("gated backward needs ypre saved by the forward"); return -11; }
   }
   return 0;
 }
-
-#define BIMAMBA_DISPATCH_I(FN, d, st)                                         \
-  switch ((d).chunk_items) {                                                  \
-    case 1: return multi ? FN<1, true>(d, st) : FN<1, false>(d, st);          \
-    case 2: return multi ? FN<2, true>(d, st) : FN<2, false>(d, st);          \
-    case 3: return multi ? FN<3, true>(d, st) : FN<3, false>(d, st);          \
-    case 4: return multi ? FN<4, true>(d, st) : FN<4, false>(d, st);          \
-    case 5: return multi ? FN<5, true>(d, st) : FN<5, false>(d, st);          \
-    case 6: return multi ? FN<6, true>(d, st) : FN<6, false>(d, st);          \
-    case 7: return multi ? FN<7, true>(d, st) : FN<7, false>(d, st);          \
-    default: return multi ? FN<8, true>(d, st) : FN<8, false>(d, st);         \
-  }
 
 }  // namespace bimamba
 
@@ -532,32 +404,32 @@ extern "C" const char* bimamba_last_error(void) { return g_err; }
 
 extern "C" int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, int* chunk_items, int* group_channels) {
   (void)backward;
-  int I = (seqlen + 31) / 32;
-  if (I < 1) I = 1;
-  if (I > 8) I = 8;
-  int G = kMaxCpw * kWarps;
-  // keep at least ~2 CTAs per SM worth of blocks when the batch is small
-  while (G > kWarps && (int64_t)rows * ((dim + G - 1) / G) < 2 * 148) G /= 2;
-  if (chunk_items) *chunk_items = I;
+  int G = kMaxG;
+  // keep at least ~3 CTAs per SM worth of blocks when the batch is small
+  while (G > 2 * kWarps && (int64_t)rows * ((dim + G - 1) / G) < 3 * 148) G /= 2;
+  if (chunk_items) *chunk_items = kT;
   if (group_channels) *group_channels = G;
-  const int tc = 32 * I;
-  return seqlen > 0 ? (seqlen + tc - 1) / tc : 1;
+  return seqlen > 0 ? (seqlen + kT - 1) / kT : 1;
 }
 
 extern "C" int bimamba_selective_scan_fwd(const bimamba_scan_desc* d, bimamba_stream_t stream) {
   if (d && (d->batch == 0 || d->seqlen == 0)) return 0;  // empty: nothing to do (pointers may be null)
   int rc = check_desc(d, false);
   if (rc) return rc;
-  const bool multi = d->seqlen > 32 * d->chunk_items;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  BIMAMBA_DISPATCH_I(launch_fwd, *d, st)
+  dim3 grid((d->dim + d->group_channels - 1) / d->group_channels, d->ndir, d->batch);
+  scan_fwd_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
 }
 
 extern "C" int bimamba_selective_scan_bwd(const bimamba_scan_desc* d, bimamba_stream_t stream) {
   if (d && (d->batch == 0 || d->seqlen == 0)) return 0;
   int rc = check_desc(d, true);
   if (rc) return rc;
-  const bool multi = d->seqlen > 32 * d->chunk_items;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  BIMAMBA_DISPATCH_I(launch_bwd, *d, st)
+  dim3 grid((d->dim + d->group_channels - 1) / d->group_channels, d->ndir, d->batch);
+  scan_bwd_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
 }

@@ -1,0 +1,73 @@
+"""CUDA-graph capture of one training / scoring step of the Bi-Mamba backend.
+
+At the Phase-6 shapes (B <= 64, L = 201) a backend step is a few hundred short kernels, so it is
+launch-latency bound; capturing it once and replaying removes the host from the
+loop.  This plays the role a tracing compiler would: explicit capture, static buffers."""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+
+class GraphedTrainStep:
+    """Captures  zero-grad -> forward -> loss -> backward [-> optimizer.step]  for a fixed input shape.
+
+    step_fn(x) must return a scalar loss tensor and must be capture-safe (no host sync).
+    `run(x)` copies x (host-pinned or device) into the static input, replays, and returns the static
+    loss tensor (read it with .item() to synchronise)."""
+
+    def __init__(self, step_fn: Callable[[torch.Tensor], torch.Tensor], example: torch.Tensor,
+                 zero_grad: Callable[[], None], optimizer: Optional[torch.optim.Optimizer] = None,
+                 warmup: int = 3):
+        self.static_x = torch.empty_like(example, device="cuda")
+        self.static_x.copy_(example)
+        self.optimizer = optimizer
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):          # lazy inits (cuBLAS handles, func attributes) happen here
+                zero_grad()
+                loss = step_fn(self.static_x)
+                loss.backward()
+                if optimizer is not None:
+                    optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            zero_grad()
+            self.static_loss = step_fn(self.static_x)
+            self.static_loss.backward()
+            if optimizer is not None:
+                optimizer.step()
+
+    def run(self, x: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x is not None:
+            self.static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
+
+
+class GraphedForward:
+    """Captures a no-grad forward (scoring, src/main.py:958-995) for a fixed input shape."""
+
+    def __init__(self, fn: Callable[[torch.Tensor], torch.Tensor], example: torch.Tensor, warmup: int = 2):
+        self.static_x = torch.empty_like(example, device="cuda")
+        self.static_x.copy_(example)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                fn(self.static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = fn(self.static_x)
+
+    def run(self, x: Optional[torch.Tensor] = None):
+        if x is not None:
+            self.static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

@@ -55,6 +55,22 @@ def _s3(t: torch.Tensor) -> Tuple[int, int, int]:
     return t.stride(0), (t.stride(1) if t.size(1) > 1 else 0), t.stride(2)
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _timed(name: str):
+    t = _lib.kernel_timer
+    return _NULL if t is None else t(name)
+
+
 def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -130,18 +146,22 @@ def scan_fwd_raw(u, delta, A, Bm, Cm, D, z, delta_bias, softplus: bool, seqlen: 
     plan = _lib.scan_plan(seqlen, dim, Bsz * ndir, want_ckpt)
     nchunks = plan[2]
     out = torch.empty((Bsz, ndir, dim, Lp), device=u.device, dtype=u.dtype)
-    ckpt = None
+    ckpt = ypre = None
     if want_ckpt and nchunks > 1:
         ckpt = torch.empty((Bsz, ndir, dim, nchunks, A.shape[1]), device=u.device, dtype=torch.float32)
+    if want_ckpt and z is not None:
+        ypre = torch.empty((Bsz, ndir, dim, Lp), device=u.device, dtype=u.dtype)
     d = _fill_desc(u, delta, A, Bm, Cm, D, z, delta_bias, softplus, seqlen, plan)
     d.out = _ptr(out)
     d.out_bs, d.out_ds, d.out_rs = _s3(out)
     d.ckpt = _ptr(ckpt)
-    _lib.check(lib.bimamba_selective_scan_fwd(C.byref(d), _stream()), "bimamba_selective_scan_fwd")
-    return out, ckpt, plan
+    d.ypre = _ptr(ypre)            # written with out's strides
+    with _timed("scan_fwd"):
+        _lib.check(lib.bimamba_selective_scan_fwd(C.byref(d), _stream()), "bimamba_selective_scan_fwd")
+    return out, ckpt, ypre, plan
 
 
-def scan_bwd_raw(u, delta, A, Bm, Cm, D, z, delta_bias, softplus: bool, seqlen: int, dout, ckpt, plan,
+def scan_bwd_raw(u, delta, A, Bm, Cm, D, z, delta_bias, softplus: bool, seqlen: int, dout, ckpt, ypre, plan,
                  dz_out=None, bc_out_dtype=None):
     """Returns (du, ddelta, dz, dBC (B, ndir, 2N, Lp), dA (dim, N), dD (dim), dbias (dim))."""
     lib = _lib.load()
@@ -164,6 +184,9 @@ def scan_bwd_raw(u, delta, A, Bm, Cm, D, z, delta_bias, softplus: bool, seqlen: 
     d.dout = _ptr(dout)
     d.out_bs, d.out_ds, d.out_rs = _s3(dout)
     d.ckpt = _ptr(ckpt)
+    d.ypre = _ptr(ypre)
+    if ypre is not None:
+        d.ypre_bs, d.ypre_ds, d.ypre_rs = _s3(ypre)
     d.du, d.ddelta, d.dz = _ptr(du), _ptr(ddelta), _ptr(dz)
     if _s3(du) != _s3(u) or _s3(ddelta) != _s3(delta):
         # du / ddelta are written with u's / delta's strides
@@ -172,7 +195,8 @@ def scan_bwd_raw(u, delta, A, Bm, Cm, D, z, delta_bias, softplus: bool, seqlen: 
         d.dz_bs, d.dz_ds, d.dz_rs = _s3(dz)
     d.dBC_part, d.dA_part, d.dD_part, d.dbias_part = _ptr(dBC_part), _ptr(dA_part), _ptr(dD_part), _ptr(db_part)
     d.dbc_rs = Lp
-    _lib.check(lib.bimamba_selective_scan_bwd(C.byref(d), _stream()), "bimamba_selective_scan_bwd")
+    with _timed("scan_bwd"):
+        _lib.check(lib.bimamba_selective_scan_bwd(C.byref(d), _stream()), "bimamba_selective_scan_bwd")
 
     dBC = torch.empty((Bsz, ndir, 2 * N, Lp), device=dev, dtype=bc_out_dtype or Bm.dtype)
     cols = 2 * N * Lp
@@ -265,12 +289,13 @@ class SelectiveScanFn(torch.autograd.Function):
         A32, D32, b32 = _f32c(A), _f32c(D), _f32c(delta_bias)
         L = u.shape[2]
         needs_bwd = any(t is not None and t.requires_grad for t in (u, delta, A, B, C, D, z, delta_bias))
-        out, ckpt, plan = scan_fwd_raw(u.unsqueeze(1), delta.unsqueeze(1), A32, Bm.unsqueeze(1), Cm.unsqueeze(1),
-                                       D32, None if zc is None else zc.unsqueeze(1), b32, bool(delta_softplus), L,
-                                       needs_bwd)
+        out, ckpt, ypre, plan = scan_fwd_raw(u.unsqueeze(1), delta.unsqueeze(1), A32, Bm.unsqueeze(1),
+                                             Cm.unsqueeze(1), D32, None if zc is None else zc.unsqueeze(1), b32,
+                                             bool(delta_softplus), L, needs_bwd)
         ctx.save_for_backward(u, delta, A32, Bm, Cm, D32 if D32 is not None else torch.empty(0),
                               zc if zc is not None else torch.empty(0), b32 if b32 is not None else torch.empty(0),
-                              ckpt if ckpt is not None else torch.empty(0))
+                              ckpt if ckpt is not None else torch.empty(0),
+                              ypre if ypre is not None else torch.empty(0))
         ctx.meta = (D is not None, z is not None, delta_bias is not None, bool(delta_softplus), plan,
                     A.dtype, None if D is None else D.dtype, None if delta_bias is None else delta_bias.dtype,
                     B.dtype, C.dtype, Bshape, Cshape, None if z is None else z.dtype)
@@ -278,17 +303,18 @@ class SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        u, delta, A32, Bm, Cm, D32, zc, b32, ckpt = ctx.saved_tensors
+        u, delta, A32, Bm, Cm, D32, zc, b32, ckpt, ypre = ctx.saved_tensors
         (hasD, hasz, hasb, softplus, plan, Adt, Ddt, bdt, Bdt, Cdt, Bshape, Cshape, zdt) = ctx.meta
         D32 = D32 if hasD else None
         zc = zc if hasz else None
         b32 = b32 if hasb else None
         ckpt = ckpt if ckpt.numel() else None
+        ypre = ypre if ypre.numel() else None
         dout = dout.to(u.dtype).contiguous()
         L = u.shape[2]
         du, ddelta, dz, dBC, dA, dD, dbias = scan_bwd_raw(
             u.unsqueeze(1), delta.unsqueeze(1), A32, Bm.unsqueeze(1), Cm.unsqueeze(1), D32,
-            None if zc is None else zc.unsqueeze(1), b32, softplus, L, dout.unsqueeze(1), ckpt, plan,
+            None if zc is None else zc.unsqueeze(1), b32, softplus, L, dout.unsqueeze(1), ckpt, ypre, plan,
             bc_out_dtype=torch.float32)
         N = A32.shape[1]
         dB = dBC[:, 0, :N].to(Bdt).reshape(Bshape)
@@ -346,13 +372,13 @@ class BiMambaInnerFn(torch.autograd.Function):
             x_dbl = torch.matmul(Wx, xc)                                      # (B, ndir, R+2N, Lp)   :73
             delta = torch.matmul(Wd, x_dbl[:, :, :R])                         # (B, ndir, D, Lp)      :80 (pre-bias)
             needs_bwd = any(ctx.needs_input_grad)
-            y, ckpt, plan = scan_fwd_raw(xc, delta, A32, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], D32,
-                                         z.unsqueeze(1), bdt32, True, L, needs_bwd)   # :82-120, :61
+            y, ckpt, ypre, plan = scan_fwd_raw(xc, delta, A32, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], D32,
+                                               z.unsqueeze(1), bdt32, True, L, needs_bwd)   # :82-120, :61
             ysum = y[:, 0] + y[:, 1] if ndir == 2 else y[:, 0]                # DualStreamSEMamba.py:481 (before out_proj)
             out = torch.matmul(ysum.transpose(1, 2)[:, :L], Wo.t())           # (B, L, dm)   mamba_block.py:62
             if needs_bwd:
                 ctx.save_for_backward(x_pad, xz, xc, x_dbl, delta, ysum, Wi, Wx, Wd, Wo, cw32, cb32, A32, D32, bdt32,
-                                      ckpt if ckpt is not None else torch.empty(0))
+                                      ckpt if ckpt is not None else torch.empty(0), ypre)
                 ctx.meta = (L, ndir, plan, x.dtype,
                             tuple(t.dtype for t in (W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out)),
                             tuple(conv_w.shape))
@@ -360,7 +386,7 @@ class BiMambaInnerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        (x_pad, xz, xc, x_dbl, delta, ysum, Wi, Wx, Wd, Wo, cw32, cb32, A32, D32, bdt32, ckpt) = ctx.saved_tensors
+        (x_pad, xz, xc, x_dbl, delta, ysum, Wi, Wx, Wd, Wo, cw32, cb32, A32, D32, bdt32, ckpt, ypre) = ctx.saved_tensors
         L, ndir, plan, xdt, pdt, cw_shape = ctx.meta
         ckpt = ckpt if ckpt.numel() else None
         with torch.autocast("cuda", enabled=False):
@@ -383,7 +409,7 @@ class BiMambaInnerFn(torch.autograd.Function):
             dyb = dy.unsqueeze(1).expand(Bsz, ndir, D, Lp)
             du, ddelta, dz2, dBC, dA, dD, dbdt = scan_bwd_raw(
                 xc, delta, A32, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], D32, z.unsqueeze(1), bdt32, True, L,
-                dyb, ckpt, plan, dz_out=dz2, bc_out_dtype=cd)
+                dyb, ckpt, ypre, plan, dz_out=dz2, bc_out_dtype=cd)
             if ndir == 2:
                 torch.add(dz2[:, 0], dz2[:, 1], out=dxz[:, D:])
             else:

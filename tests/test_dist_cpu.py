@@ -1,0 +1,80 @@
+"""world_size-2 gloo test of the host-side data-parallel logic (no GPU): batch sharding and the
+flat-bucket gradient all-reduce must reproduce the single-process full-batch gradient."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import importlib
+
+pkg = importlib.import_module("robust-audio-deepfake-evolution_b200")
+from importlib import import_module
+
+dmod = import_module("robust-audio-deepfake-evolution_b200.dist")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _make_model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 3))
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = _make_model()
+    bucket = dmod.FlatGradBucket(model.parameters())
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(10, 12, generator=g)
+    y = torch.randn(10, 3, generator=g)
+    lo, hi = dmod.shard_batch(10, rank, world)
+    bucket.zero()
+    # local mean over the shard, weighted so that the average over ranks is the global mean
+    loss = ((model(x[lo:hi]) - y[lo:hi]) ** 2).sum() / (10 / world)
+    loss.backward()
+    flat = bucket.all_reduce_mean().clone()
+    if rank == 0:
+        q.put(flat)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_batch_covers_everything():
+    for gb in (8, 10, 256, 7):
+        for world in (1, 2, 4, 8):
+            spans = [dmod.shard_batch(gb, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == gb
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_flat_bucket_allreduce_matches_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flat = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    model = _make_model()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(10, 12, generator=g)
+    y = torch.randn(10, 3, generator=g)
+    (((model(x) - y) ** 2).sum() / 10).backward()
+    ref = torch.cat([p.grad.flatten() for p in model.parameters()])
+    assert torch.allclose(flat, ref, rtol=1e-5, atol=1e-6)
