@@ -9,13 +9,15 @@
  * :455, called at :473 and :477); the in-repo statement of the same math is
  * src/models/modules/mamba_block.py.  The FFI the reference's path binds upstream is
  * `selective_scan_cuda.{fwd,bwd}` and `causal_conv1d_cuda.causal_conv1d_{fwd,bwd}`;
- * the functions below are their drop-in equivalents (same operand meaning, channel-
- * first (B, D, L) operands), extended with a direction axis so that the forward scan
- * and the flipped scan of DualStreamSEMamba.py:473-481 share ONE launch.
+ * the functions below are their drop-in equivalents (same operand meaning), with two
+ * B200-first changes: (1) activations are CHANNEL-LAST (batch, time, channel) - the
+ * layout the in_proj / x_proj / out_proj GEMMs produce and consume - so the path has
+ * no transposes, and (2) a direction axis lets the forward scan and the flipped scan
+ * of DualStreamSEMamba.py:473-481 share ONE launch with no flipped copies.
  *
  *   bimamba_causal_conv1d_fwd/bwd    <- mamba_block.py:24-31,52-55 (depthwise causal
  *                                       Conv1d k=4, crop to L, SiLU) and its autograd
- *   bimamba_selective_scan_fwd/bwd   <- mamba_block.py:80 (softplus), :82 (A),
+ *   bimamba_selective_scan_fwd/bwd   <- mamba_block.py:80 (dt_proj + softplus), :82 (A),
  *                                       :92-117 (scan), :120 (D skip), :61 (z gate)
  *                                       and its autograd
  *   bimamba_reduce_partials          <- the sum over batch/time/direction that
@@ -37,7 +39,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 2
+#define BIMAMBA_ABI_VERSION 3
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -46,84 +48,100 @@ extern "C" {
 
 /* flags */
 #define BIMAMBA_FLAG_SOFTPLUS 1 /* delta = softplus(delta + delta_bias) (mamba_block.py:80) */
+#define BIMAMBA_FLAG_DTR_PADDED 2 /* scan: every dtr row is readable (and finite) up to 16 elements and
+                                    16-byte aligned, so it can be staged with vector copies */
 #define BIMAMBA_FLAG_SILU 1     /* conv: apply SiLU (mamba_block.py:55) */
+
+#define BIMAMBA_DSTATE 16       /* d_state of the Phase-6 configuration (Phase6_Proposed.conf:26) */
+#define BIMAMBA_MAX_DT_RANK 16
+#define BIMAMBA_CHUNK 16        /* steps per chunk = checkpoint interval */
 
 typedef void* bimamba_stream_t; /* a cudaStream_t */
 
-/* Strides are in ELEMENTS.  "dir" is the direction axis: dir 0 scans t = 0..L-1,
- * dir 1 scans t = L-1..0 on the same storage order (natural time order in memory), i.e.
- * dir 1 computes flip(op(flip(.))) of DualStreamSEMamba.py:476-478 without any flipped copy. */
+/* Selective scan.  All activations are channel-last and share the element type io_dtype:
+ * element (b, dir, t, d) of tensor X lives at X + b*X_bs + dir*X_ds + t*X_ts + d (unit
+ * channel stride; strides in ELEMENTS).  "dir" is the direction axis: dir 0 scans
+ * t = 0..L-1, dir 1 scans t = L-1..0 over the same storage (natural time order in memory),
+ * i.e. dir 1 computes flip(op(flip(.))) of DualStreamSEMamba.py:476-478 with no flipped copy.
+ * A stride of 0 on the dir axis shares one tensor between both directions (z, dout).
+ *
+ * The step size is either given (delta != NULL: the dt_proj output before bias and
+ * softplus, as in mamba_ssm's selective_scan_fn) or produced in-kernel from the low-rank
+ * projection (delta == NULL:  delta_raw[t,d] = sum_r Wdt[d,r] * dtr[t,r], mamba_block.py:80),
+ * which saves writing and re-reading a (B, L, D) tensor. */
 typedef struct bimamba_scan_desc {
-  /* activations, element type io_dtype */
-  const void* u;     /* (batch, ndir, dim, L)   conv output xc          */
-  const void* delta; /* (batch, ndir, dim, L)   dt_proj output, pre-softplus */
-  const void* z;     /* (batch, ndir, dim, L) or NULL (gate input; z_ds may be 0 to share) */
-  const void* Bm;    /* (batch, ndir, dstate, L), element type bc_dtype */
-  const void* Cm;    /* (batch, ndir, dstate, L), element type bc_dtype */
-  const float* A;    /* (dim, dstate) fp32, = -exp(A_log)               */
-  const float* D;    /* (dim) fp32 or NULL                              */
-  const float* delta_bias; /* (dim) fp32 or NULL                        */
-  void* out;         /* fwd: (batch, ndir, dim, L) io_dtype              */
-  float* ckpt;       /* (batch, ndir, dim, nchunks, dstate) fp32 state entering each 16-step chunk;
-                        written by fwd (may be NULL when nchunks == 1 or no backward is
-                        needed), read by bwd when nchunks > 1             */
-  void* ypre;        /* (batch, ndir, dim, L) io_dtype, strides ypre_*: y before the z gate.
-                        Written by fwd when non-NULL; read by bwd to form dz (required there
-                        when z and dz are given)                          */
+  const void* u;     /* (batch, ndir, L, dim)   conv output xc                          */
+  const void* z;     /* (batch, ndir, L, dim) or NULL (gate input)                       */
+  const void* delta; /* (batch, ndir, L, dim) or NULL (then dtr / Wdt are used)          */
+  const void* bc;    /* (batch, ndir, L, 32): row t = [B_t(16) | C_t(16)]                */
+  const void* dtr;   /* (batch, ndir, L, dt_rank) low-rank step-size features, or NULL   */
+  const float* Wdt;  /* (dim, dt_rank) fp32 dt_proj.weight, or NULL                      */
+  const float* A;    /* (dim, 16) fp32, = -exp(A_log)                                    */
+  const float* D;    /* (dim) fp32 or NULL                                               */
+  const float* delta_bias; /* (dim) fp32 or NULL                                         */
+  void* out;         /* fwd: (batch, ndir, L, dim) gated output                          */
+  void* ypre;        /* (batch, ndir, L, dim) y before the z gate, strides = out's.  Written by
+                        fwd when non-NULL; read by bwd to form dz (required there with z) */
+  float* ckpt;       /* (batch, ndir, nchunks, dim, 16) fp32 state entering each 16-step chunk;
+                        written by fwd when non-NULL, read by bwd when nchunks > 1        */
   /* backward only */
-  const void* dout;  /* (batch, ndir, dim, L) io_dtype, strides = out's  */
-  void* du;          /* (batch, ndir, dim, L) io_dtype, strides = u's    */
-  void* ddelta;      /* same, strides = delta's                          */
-  void* dz;          /* same or NULL; strides dz_bs/dz_ds/dz_rs          */
-  float* dBC_part;   /* (batch, ndir, ngroups, 2, dstate, dbc_rs) fp32 partial sums over each
-                        channel group; reduce over ngroups with bimamba_reduce_partials */
-  float* dA_part;    /* (batch, ndir, dim, dstate) fp32                  */
-  float* dD_part;    /* (batch, ndir, dim) fp32 or NULL                  */
-  float* dbias_part; /* (batch, ndir, dim) fp32 or NULL                  */
+  const void* dout;  /* (batch, ndir, L, dim), strides dout_*                             */
+  void* du;          /* (batch, ndir, L, dim), strides = out's (out_bs/out_ds/out_ts)     */
+  void* ddelta;      /* same layout: gradient w.r.t. the pre-softplus step size           */
+  void* dz;          /* same layout or NULL: per-direction gradient of the gate input     */
+  float* dbc_part;   /* (batch, ngroups, L, ndir, 32) fp32 partial [dB | dC] of each channel
+                        group; reduce over ngroups with bimamba_reduce_partials -> rows
+                        ordered (batch, time, dir)                                        */
+  float* dA_part;    /* (batch, ndir, dim, 16) fp32                                        */
+  float* dD_part;    /* (batch, ndir, dim) fp32 or NULL                                    */
+  float* dbias_part; /* (batch, ndir, dim) fp32 or NULL                                    */
 
-  int32_t batch, ndir, dim, seqlen, dstate;
-  int32_t io_dtype, bc_dtype, flags;
-  int32_t chunk_items;   /* steps per chunk = checkpoint interval (16);
-                            nchunks = ceil(seqlen / chunk_items).  Use bimamba_scan_plan(). */
-  int32_t group_channels;/* channels per CTA (even, 2..32); ngroups = ceil(dim / group_channels) */
-  int32_t pad_to;        /* if > seqlen: columns [seqlen, pad_to) of every activation output
-                            (out; du, ddelta, dz) are written as zeros, so padded rows can be
-                            fed to GEMMs that contract over time                */
+  int32_t batch, ndir, dim, seqlen, dstate, dt_rank;
+  int32_t io_dtype, flags;
+  int32_t group_channels; /* channels per CTA (use bimamba_scan_plan) */
   int32_t reserved0;
-  int64_t u_bs, u_ds, u_rs;
-  int64_t delta_bs, delta_ds, delta_rs;
-  int64_t z_bs, z_ds, z_rs;
-  int64_t bc_bs, bc_ds, bc_rs;
-  int64_t out_bs, out_ds, out_rs;
-  int64_t dz_bs, dz_ds, dz_rs;
-  int64_t dbc_rs;        /* row stride of dBC_part (>= seqlen); columns [seqlen, dbc_rs) are zeroed */
-  int64_t ypre_bs, ypre_ds, ypre_rs;
+  int64_t u_bs, u_ds, u_ts;
+  int64_t z_bs, z_ds, z_ts;
+  int64_t delta_bs, delta_ds, delta_ts;
+  int64_t bc_bs, bc_ds, bc_ts;
+  int64_t dtr_bs, dtr_ds, dtr_ts;
+  int64_t out_bs, out_ds, out_ts;
+  int64_t dout_bs, dout_ds, dout_ts;
 } bimamba_scan_desc;
 
 int bimamba_abi_version(void);
 const char* bimamba_last_error(void);
 
-/* Fills chunk_items / group_channels for (seqlen, dim, batch*ndir); returns nchunks. */
-int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, int* chunk_items, int* group_channels);
+/* Chooses the channel-group width for (seqlen, dim, batch*ndir); backward != 0 selects the
+ * backward kernel's geometry.  Returns nchunks = ceil(seqlen / 16); *ngroups = CTAs per
+ * (batch, dir) = ceil(dim / *group_channels). */
+int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, int* group_channels, int* ngroups);
 
 int bimamba_selective_scan_fwd(const bimamba_scan_desc* d, bimamba_stream_t stream);
 int bimamba_selective_scan_bwd(const bimamba_scan_desc* d, bimamba_stream_t stream);
 
-/* Depthwise causal conv (dir 0: taps t-(K-1)..t; dir 1: taps t..t+(K-1), i.e. the causal conv
- * of the time-reversed sequence), K in {2,3,4}.  x: (batch, dim, L); out: (batch, ndir, dim, L).
- * Output columns [seqlen, pad_to) are zero-filled when pad_to > seqlen. */
-int bimamba_causal_conv1d_fwd(const void* x, const float* weight /*(dim,K)*/, const float* bias /*(dim) or NULL*/,
-                              void* out, int batch, int ndir, int dim, int seqlen, int pad_to, int width,
-                              int64_t x_bs, int64_t x_rs, int64_t out_bs, int64_t out_ds, int64_t out_rs,
+/* Depthwise causal conv, channel-last.  x: (batch, L, dim) with strides x_bs, x_ts;
+ * out: (batch, ndir, L, dim) with strides out_bs, out_ds, out_ts.  dir 0: taps t-(K-1)..t;
+ * dir 1: taps t..t+(K-1), i.e. the causal conv of the time-reversed sequence in natural
+ * order.  K in {2,3,4}; weight (dim, K) fp32; bias (dim) fp32 or NULL. */
+int bimamba_causal_conv1d_fwd(const void* x, const float* weight, const float* bias, void* out,
+                              int batch, int ndir, int dim, int seqlen, int width,
+                              int64_t x_bs, int64_t x_ts, int64_t out_bs, int64_t out_ds, int64_t out_ts,
                               int dtype, int flags, bimamba_stream_t stream);
 
-/* dout: (batch, ndir, dim, L) grads w.r.t. the conv output of each direction.
- * dx: (batch, dim, L) (sum over directions).  dwb_part: (batch, dim, K+1) fp32 partials
- * [dw_0..dw_{K-1}, dbias] per (batch, channel); reduce over batch with bimamba_reduce_partials. */
+/* dout: (batch, ndir, L, dim) grads w.r.t. the conv output of each direction.
+ * dx: (batch, L, dim), summed over directions.  dz_in (optional, may be NULL): per-direction
+ * (batch, ndir, L, dim) gate gradients with dout's strides; when given their sum over
+ * directions is written to dz_out (batch, L, dim) with dx's strides, so the in_proj backward
+ * reads one [dx | dz] matrix.  dwb_part: (nslices, dim, K+1) fp32 partials
+ * [dw_0..dw_{K-1}, dbias] with nslices = bimamba_conv_bwd_slices(batch, seqlen); reduce over
+ * slices with bimamba_reduce_partials. */
+int bimamba_conv_bwd_slices(int batch, int seqlen);
 int bimamba_causal_conv1d_bwd(const void* x, const float* weight, const float* bias, const void* dout,
-                              void* dx, float* dwb_part, int batch, int ndir, int dim, int seqlen, int pad_to, int width,
-                              int64_t x_bs, int64_t x_rs, int64_t dout_bs, int64_t dout_ds, int64_t dout_rs,
-                              int64_t dx_bs, int64_t dx_rs, int dtype, int flags, bimamba_stream_t stream);
+                              void* dx, const void* dz_in, void* dz_out, float* dwb_part,
+                              int batch, int ndir, int dim, int seqlen, int width,
+                              int64_t x_bs, int64_t x_ts, int64_t dout_bs, int64_t dout_ds, int64_t dout_ts,
+                              int64_t dx_bs, int64_t dx_ts, int dtype, int flags, bimamba_stream_t stream);
 
 /* For every g < groups:  out[g*out_gs + j] (+)= sum_{i < rows} part[g*part_gs + i*row_stride + j],
  * j < cols, summed in fixed order (deterministic).  out element type out_dtype;

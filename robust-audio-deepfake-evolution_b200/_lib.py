@@ -13,13 +13,16 @@ LIB_PATH = os.path.join(HERE, "libbimamba_sm100.so")
 
 F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
+FLAG_DTR_PADDED = 2
 FLAG_SILU = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
+CHUNK = 16
 
 EXPORTS = (
     "bimamba_abi_version", "bimamba_last_error", "bimamba_scan_plan",
     "bimamba_selective_scan_fwd", "bimamba_selective_scan_bwd",
-    "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_reduce_partials",
+    "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_conv_bwd_slices",
+    "bimamba_reduce_partials",
 )
 
 
@@ -27,15 +30,15 @@ class ScanDesc(C.Structure):
     """Mirror of `struct bimamba_scan_desc` (include/bimamba.h)."""
     _fields_ = (
         [(n, C.c_void_p) for n in (
-            "u", "delta", "z", "Bm", "Cm", "A", "D", "delta_bias", "out", "ckpt", "ypre",
-            "dout", "du", "ddelta", "dz", "dBC_part", "dA_part", "dD_part", "dbias_part")]
+            "u", "z", "delta", "bc", "dtr", "Wdt", "A", "D", "delta_bias", "out", "ypre", "ckpt",
+            "dout", "du", "ddelta", "dz", "dbc_part", "dA_part", "dD_part", "dbias_part")]
         + [(n, C.c_int32) for n in (
-            "batch", "ndir", "dim", "seqlen", "dstate", "io_dtype", "bc_dtype", "flags",
-            "chunk_items", "group_channels", "pad_to", "reserved0")]
+            "batch", "ndir", "dim", "seqlen", "dstate", "dt_rank", "io_dtype", "flags",
+            "group_channels", "reserved0")]
         + [(n, C.c_int64) for n in (
-            "u_bs", "u_ds", "u_rs", "delta_bs", "delta_ds", "delta_rs", "z_bs", "z_ds", "z_rs",
-            "bc_bs", "bc_ds", "bc_rs", "out_bs", "out_ds", "out_rs", "dz_bs", "dz_ds", "dz_rs", "dbc_rs",
-            "ypre_bs", "ypre_ds", "ypre_rs")]
+            "u_bs", "u_ds", "u_ts", "z_bs", "z_ds", "z_ts", "delta_bs", "delta_ds", "delta_ts",
+            "bc_bs", "bc_ds", "bc_ts", "dtr_bs", "dtr_ds", "dtr_ts", "out_bs", "out_ds", "out_ts",
+            "dout_bs", "dout_ds", "dout_ts")]
     )
 
 
@@ -76,11 +79,13 @@ def load() -> C.CDLL:
             fn.restype = i32
             fn.argtypes = [C.POINTER(ScanDesc), vp]
         lib.bimamba_causal_conv1d_fwd.restype = i32
-        lib.bimamba_causal_conv1d_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
+        lib.bimamba_causal_conv1d_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                                   i64, i64, i64, i64, i64, i32, i32, vp]
         lib.bimamba_causal_conv1d_bwd.restype = i32
-        lib.bimamba_causal_conv1d_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
+        lib.bimamba_causal_conv1d_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                                   i64, i64, i64, i64, i64, i64, i64, i32, i32, vp]
+        lib.bimamba_conv_bwd_slices.restype = i32
+        lib.bimamba_conv_bwd_slices.argtypes = [i32, i32]
         lib.bimamba_reduce_partials.restype = i32
         lib.bimamba_reduce_partials.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp]
         got = lib.bimamba_abi_version()
@@ -99,7 +104,7 @@ def check(rc: int, what: str) -> None:
 
 
 def scan_plan(seqlen: int, dim: int, rows: int, backward: bool = False):
-    """-> (chunk_items, group_channels, nchunks)"""
-    ci, gc = C.c_int(0), C.c_int(0)
-    n = load().bimamba_scan_plan(int(seqlen), int(dim), int(rows), int(backward), C.byref(ci), C.byref(gc))
-    return ci.value, gc.value, n
+    """-> (group_channels, ngroups, nchunks)"""
+    gc, ng = C.c_int(0), C.c_int(0)
+    n = load().bimamba_scan_plan(int(seqlen), int(dim), int(rows), int(backward), C.byref(gc), C.byref(ng))
+    return gc.value, ng.value, n

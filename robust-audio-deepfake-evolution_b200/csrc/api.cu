@@ -1,0 +1,58 @@
+// Host-side pieces of the C ABI shared by the kernels: error string, descriptor checks, launch plan.
+#include "common.cuh"
+
+namespace bimamba {
+
+thread_local char g_err[512] = "";
+void set_err(const char* msg) {
+  size_t i = 0;
+  for (; msg[i] && i + 1 < sizeof(g_err); ++i) g_err[i] = msg[i];
+  g_err[i] = 0;
+}
+
+int check_desc(const bimamba_scan_desc* d, bool bwd) {
+  if (!d) { set_err("null descriptor"); return -1; }
+  if (d->dstate != kN) { set_err("dstate must be 16"); return -2; }
+  if (d->batch < 0 || d->ndir < 1 || d->ndir > 2 || d->dim < 1 || d->seqlen < 0) { set_err("bad sizes"); return -3; }
+  if (d->batch > 65535) { set_err("batch > 65535 not supported by this launch geometry"); return -3; }
+  if (d->io_dtype < 0 || d->io_dtype > 2) { set_err("bad dtype"); return -6; }
+  if (!d->u || !d->A || !d->bc) { set_err("null operand"); return -7; }
+  if (!d->delta) {
+    if (!d->dtr || !d->Wdt) { set_err("either delta or (dtr, Wdt) must be given"); return -7; }
+    if (d->dt_rank < 1 || d->dt_rank > BIMAMBA_MAX_DT_RANK) { set_err("dt_rank must be 1..16"); return -4; }
+  }
+  if (!bwd && !d->out) { set_err("null out"); return -7; }
+  if (bwd) {
+    if (!d->dout || !d->du || !d->ddelta || !d->dbc_part || !d->dA_part) { set_err("null backward operand"); return -8; }
+    if (d->seqlen > kT && !d->ckpt) { set_err("backward needs the forward checkpoints"); return -9; }
+    if (d->z && d->dz && !d->ypre) { set_err("gated backward needs ypre saved by the forward"); return -11; }
+  }
+  return 0;
+}
+
+}  // namespace bimamba
+
+using namespace bimamba;
+
+extern "C" int bimamba_abi_version(void) { return BIMAMBA_ABI_VERSION; }
+extern "C" const char* bimamba_last_error(void) { return g_err; }
+
+extern "C" int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, int* group_channels, int* ngroups) {
+  int G;
+  if (backward) {
+    G = 32;
+    // keep at least ~3 CTAs per SM worth of blocks when the batch is small
+    while (G > 8 && (int64_t)rows * ((dim + G - 1) / G) < 3 * 148) G /= 2;
+  } else {
+    // one thread per channel: wide groups share the staged B|C|dt_r rows, narrow ones fill the GPU
+    G = 32;
+    const int cand[3] = {128, 96, 64};
+    for (int i = 0; i < 3; ++i) {
+      const int g = cand[i];
+      if (dim % g == 0 && (int64_t)rows * (dim / g) >= 4 * 148) { G = g; break; }
+    }
+  }
+  if (group_channels) *group_channels = G;
+  if (ngroups) *ngroups = (dim + G - 1) / G;
+  return seqlen > 0 ? (seqlen + kT - 1) / kT : 1;
+}

@@ -10,7 +10,13 @@ Public names mirror what the reference's path binds upstream:
     (src/models/DualStreamSEMamba.py:473-481 around mamba_block.py:41-63)
 
 All arithmetic runs in the CUDA library (ops on CPU tensors raise: there is no fallback).
-Activations are channel-first (batch, dim, L) like the upstream ops.
+
+Layout.  The kernels are channel-last: every activation is (batch, time, channel) with unit channel
+stride, the layout the projections produce and consume, so the block has no transposes.  Tensors
+that exist once per direction are stored (batch, time, dir, channel) and handed to the kernels as
+(batch, dir, time, channel) VIEWS (the C ABI takes element strides), which makes
+``y.view(B*L, 2*D)`` the operand of ONE out_proj GEMM over both directions.  The op-level functions
+keep the upstream (batch, channel, time) signature and transpose at the boundary.
 """
 from __future__ import annotations
 
@@ -24,6 +30,8 @@ from ._lib import ScanDesc
 
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
 D_STATE = 16
+MAX_DT_RANK = 16
+XW = 48          # row of the padded x_proj output: [B(16) | C(16) | dt_r (<= 16, zero padded)]
 
 
 def _require_cuda(*ts):
@@ -48,10 +56,10 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _s3(t: torch.Tensor) -> Tuple[int, int, int]:
-    """(batch, dir, row) element strides of a (batch, ndir, rows, L) tensor with unit inner stride."""
+    """(batch, dir, time) element strides of a (batch, ndir, L, C) tensor with unit channel stride."""
     assert t.dim() == 4
-    if t.size(3) > 1 and t.stride(3) != 1:
-        raise ValueError("time must be the contiguous (innermost) axis")
+    if t.numel() and t.size(3) > 1 and t.stride(3) != 1:
+        raise ValueError("channels must be the contiguous (innermost) axis")
     return t.stride(0), (t.stride(1) if t.size(1) > 1 else 0), t.stride(2)
 
 
@@ -71,137 +79,153 @@ def _timed(name: str):
     return _NULL if t is None else t(name)
 
 
-def round_up(x: int, m: int) -> int:
-    return (x + m - 1) // m * m
-
-
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def per_dir(Bsz: int, L: int, ndir: int, C_: int, device, dtype, zero: bool = False) -> torch.Tensor:
+    """Allocates (B, L, ndir, C) storage and returns the (B, ndir, L, C) view the kernels take."""
+    mk = torch.zeros if zero else torch.empty
+    return mk((Bsz, L, ndir, C_), device=device, dtype=dtype).permute(0, 2, 1, 3)
+
+
+def rows2d(t: torch.Tensor) -> torch.Tensor:
+    """(B, ndir, L, C) view of (B, L, ndir, C) storage -> the (B*L*ndir, C) row matrix (no copy)."""
+    Bsz, ndir, L, C_ = t.shape
+    return t.permute(0, 2, 1, 3).reshape(Bsz * L * ndir, C_)
 
 
 # ----------------------------------------------------------------------------------------
 # raw kernels (no autograd)
 # ----------------------------------------------------------------------------------------
-def conv_fwd_raw(x, weight, bias, out, seqlen: int, silu: bool):
-    """x (B, D, >=L) strided; weight (D, K) fp32; out (B, ndir, D, Lp) strided."""
+def conv_fwd_raw(x, weight, bias, out, silu: bool):
+    """x (B, L, D) with unit channel stride; weight (D, K) fp32; out (B, ndir, L, D) view."""
     lib = _lib.load()
-    B, D = x.shape[0], x.shape[1]
-    ndir, Lp = out.shape[1], out.shape[3]
-    obs, ods, ors = _s3(out)
-    rc = lib.bimamba_causal_conv1d_fwd(
-        _ptr(x), _ptr(weight), _ptr(bias), _ptr(out), B, ndir, D, seqlen, Lp, weight.shape[1],
-        x.stride(0), x.stride(1), obs, ods, ors, _dt(x), _lib.FLAG_SILU if silu else 0, _stream())
-    _lib.check(rc, "bimamba_causal_conv1d_fwd")
+    Bsz, L, D = x.shape
+    ndir = out.shape[1]
+    obs, ods, ots = _s3(out)
+    if x.stride(2) != 1 and D > 1:
+        raise ValueError("x must have unit channel stride")
+    with _timed("conv_fwd"):
+        rc = lib.bimamba_causal_conv1d_fwd(
+            _ptr(x), _ptr(weight), _ptr(bias), _ptr(out), Bsz, ndir, D, L, weight.shape[1],
+            x.stride(0), x.stride(1), obs, ods, ots, _dt(x), _lib.FLAG_SILU if silu else 0, _stream())
+        _lib.check(rc, "bimamba_causal_conv1d_fwd")
 
 
-def conv_bwd_raw(x, weight, bias, dout, dx, seqlen: int, silu: bool):
-    """dout (B, ndir, D, Lp); dx (B, D, Lp) strided.  Returns dwb (D, K+1) fp32 [dw | dbias]."""
+def conv_bwd_raw(x, weight, bias, dout, dx, silu: bool, dz_in=None, dz_out=None):
+    """dout (B, ndir, L, D) view; dx (B, L, D) (may be a strided view).  Optionally folds the sum of the
+    per-direction gate gradients dz_in (same strides as dout) into dz_out (same strides as dx).
+    Returns dwb (D, K+1) fp32 [dw | dbias]."""
     lib = _lib.load()
-    B, D = x.shape[0], x.shape[1]
+    Bsz, L, D = x.shape
     ndir = dout.shape[1]
     K = weight.shape[1]
-    gbs, gds, grs = _s3(dout)
-    part = torch.empty((B, D, K + 1), device=x.device, dtype=torch.float32)
-    rc = lib.bimamba_causal_conv1d_bwd(
-        _ptr(x), _ptr(weight), _ptr(bias), _ptr(dout), _ptr(dx), _ptr(part), B, ndir, D, seqlen, dx.shape[2], K,
-        x.stride(0), x.stride(1), gbs, gds, grs, dx.stride(0), dx.stride(1), _dt(x),
-        _lib.FLAG_SILU if silu else 0, _stream())
-    _lib.check(rc, "bimamba_causal_conv1d_bwd")
+    gbs, gds, gts = _s3(dout)
+    if dz_in is not None:
+        if _s3(dz_in) != (gbs, gds, gts):
+            raise ValueError("dz_in must share dout's strides")
+        if (dz_out.stride(0), dz_out.stride(1)) != (dx.stride(0), dx.stride(1)):
+            raise ValueError("dz_out must share dx's strides")
+    nsl = lib.bimamba_conv_bwd_slices(Bsz, L)
+    part = torch.empty((max(nsl, 1), D, K + 1), device=x.device, dtype=torch.float32)
+    with _timed("conv_bwd"):
+        rc = lib.bimamba_causal_conv1d_bwd(
+            _ptr(x), _ptr(weight), _ptr(bias), _ptr(dout), _ptr(dx), _ptr(dz_in), _ptr(dz_out), _ptr(part),
+            Bsz, ndir, D, L, K, x.stride(0), x.stride(1), gbs, gds, gts, dx.stride(0), dx.stride(1), _dt(x),
+            _lib.FLAG_SILU if silu else 0, _stream())
+        _lib.check(rc, "bimamba_causal_conv1d_bwd")
     dwb = torch.empty((D, K + 1), device=x.device, dtype=torch.float32)
-    reduce_raw(part, dwb, groups=1, rows=B, cols=D * (K + 1), part_gs=0, row_stride=D * (K + 1), out_gs=0)
+    if Bsz * L == 0:
+        return dwb.zero_()
+    reduce_raw(part, dwb, groups=1, rows=nsl, cols=D * (K + 1), part_gs=0, row_stride=D * (K + 1), out_gs=0)
     return dwb
 
 
 def reduce_raw(part, out, groups, rows, cols, part_gs, row_stride, out_gs, accumulate=False):
     lib = _lib.load()
-    rc = lib.bimamba_reduce_partials(_ptr(part), _ptr(out), groups, rows, cols, part_gs, row_stride, out_gs,
-                                     _dt(out), int(accumulate), _stream())
-    _lib.check(rc, "bimamba_reduce_partials")
+    with _timed("reduce"):
+        rc = lib.bimamba_reduce_partials(_ptr(part), _ptr(out), groups, rows, cols, part_gs, row_stride, out_gs,
+                                         _dt(out), int(accumulate), _stream())
+        _lib.check(rc, "bimamba_reduce_partials")
 
 
-def _fill_desc(u, delta, A, Bm, Cm, D, z, delta_bias, softplus, seqlen, plan) -> ScanDesc:
+def _fill_desc(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus, dtr_padded, G) -> ScanDesc:
     d = ScanDesc()
-    Bsz, ndir, dim, Lp = u.shape
-    d.u, d.delta, d.z = _ptr(u), _ptr(delta), _ptr(z)
-    d.Bm, d.Cm, d.A, d.D, d.delta_bias = _ptr(Bm), _ptr(Cm), _ptr(A), _ptr(D), _ptr(delta_bias)
-    d.batch, d.ndir, d.dim, d.seqlen, d.dstate = Bsz, ndir, dim, seqlen, A.shape[1]
-    d.io_dtype, d.bc_dtype = _dt(u), _dt(Bm)
-    d.flags = _lib.FLAG_SOFTPLUS if softplus else 0
-    d.chunk_items, d.group_channels = plan[0], plan[1]
-    d.pad_to = Lp
-    d.u_bs, d.u_ds, d.u_rs = _s3(u)
-    d.delta_bs, d.delta_ds, d.delta_rs = _s3(delta)
-    if z is not None:
-        d.z_bs, d.z_ds, d.z_rs = _s3(z)
-    d.bc_bs, d.bc_ds, d.bc_rs = _s3(Bm)
-    if _s3(Cm) != _s3(Bm):
-        raise ValueError("B and C must share strides")
+    Bsz, ndir, L, dim = u.shape
+    d.u, d.z, d.delta, d.bc, d.dtr = _ptr(u), _ptr(z), _ptr(delta), _ptr(bc), _ptr(dtr)
+    d.Wdt, d.A, d.D, d.delta_bias = _ptr(Wdt), _ptr(A), _ptr(D), _ptr(delta_bias)
+    d.batch, d.ndir, d.dim, d.seqlen, d.dstate = Bsz, ndir, dim, L, A.shape[1]
+    d.dt_rank = 0 if Wdt is None else Wdt.shape[1]
+    d.io_dtype = _dt(u)
+    d.flags = (_lib.FLAG_SOFTPLUS if softplus else 0) | (_lib.FLAG_DTR_PADDED if dtr_padded else 0)
+    d.group_channels = G
+    d.u_bs, d.u_ds, d.u_ts = _s3(u)
+    for name, t in (("z", z), ("delta", delta), ("bc", bc), ("dtr", dtr)):
+        if t is not None:
+            if t.dtype != u.dtype:
+                raise TypeError(f"{name} must have u's dtype")
+            bs, ds, ts = _s3(t)
+            setattr(d, name + "_bs", bs), setattr(d, name + "_ds", ds), setattr(d, name + "_ts", ts)
     return d
 
 
-def scan_fwd_raw(u, delta, A, Bm, Cm, D, z, delta_bias, softplus: bool, seqlen: int, want_ckpt: bool):
-    """All activations 4-D (B, ndir, rows, Lp) with unit inner stride.  Returns (out, ckpt, plan)."""
+def scan_fwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, want_ckpt: bool,
+                 dtr_padded: bool = False):
+    """All activations are (B, ndir, L, C) views with unit channel stride (z may be expanded over
+    dir).  Returns (out, ckpt, ypre): out / ypre are (B, ndir, L, dim) views of (B, L, ndir, dim)."""
     lib = _lib.load()
-    Bsz, ndir, dim, Lp = u.shape
-    plan = _lib.scan_plan(seqlen, dim, Bsz * ndir, want_ckpt)
-    nchunks = plan[2]
-    out = torch.empty((Bsz, ndir, dim, Lp), device=u.device, dtype=u.dtype)
+    Bsz, ndir, L, dim = u.shape
+    G, ngroups, nchunks = _lib.scan_plan(L, dim, Bsz * ndir, False)
+    out = per_dir(Bsz, L, ndir, dim, u.device, u.dtype)
     ckpt = ypre = None
     if want_ckpt and nchunks > 1:
-        ckpt = torch.empty((Bsz, ndir, dim, nchunks, A.shape[1]), device=u.device, dtype=torch.float32)
+        ckpt = torch.empty((Bsz, ndir, nchunks, dim, A.shape[1]), device=u.device, dtype=torch.float32)
     if want_ckpt and z is not None:
-        ypre = torch.empty((Bsz, ndir, dim, Lp), device=u.device, dtype=u.dtype)
-    d = _fill_desc(u, delta, A, Bm, Cm, D, z, delta_bias, softplus, seqlen, plan)
-    d.out = _ptr(out)
-    d.out_bs, d.out_ds, d.out_rs = _s3(out)
-    d.ckpt = _ptr(ckpt)
-    d.ypre = _ptr(ypre)            # written with out's strides
+        ypre = per_dir(Bsz, L, ndir, dim, u.device, u.dtype)
+    d = _fill_desc(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus, dtr_padded, G)
+    d.out, d.ypre, d.ckpt = _ptr(out), _ptr(ypre), _ptr(ckpt)
+    d.out_bs, d.out_ds, d.out_ts = _s3(out)
     with _timed("scan_fwd"):
         _lib.check(lib.bimamba_selective_scan_fwd(C.byref(d), _stream()), "bimamba_selective_scan_fwd")
-    return out, ckpt, ypre, plan
+    return out, ckpt, ypre
 
 
-def scan_bwd_raw(u, delta, A, Bm, Cm, D, z, delta_bias, softplus: bool, seqlen: int, dout, ckpt, ypre, plan,
-                 dz_out=None, bc_out_dtype=None):
-    """Returns (du, ddelta, dz, dBC (B, ndir, 2N, Lp), dA (dim, N), dD (dim), dbias (dim))."""
+def scan_bwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, dout, ckpt, ypre,
+                 dtr_padded: bool = False, bc_out_dtype=None):
+    """Returns (du, ddelta, dz, dbc, dA, dD, dbias): du / ddelta / dz are (B, ndir, L, dim) views of
+    (B, L, ndir, dim) storage; dbc is (B, ndir, L, 32) = [dB | dC] likewise; dA (dim, N), dD, dbias (dim)."""
     lib = _lib.load()
-    Bsz, ndir, dim, Lp = u.shape
+    Bsz, ndir, L, dim = u.shape
     N = A.shape[1]
-    G = plan[1]
-    ngroups = (dim + G - 1) // G
     dev = u.device
-    du = torch.empty_like(u)
-    ddelta = torch.empty((Bsz, ndir, dim, Lp), device=dev, dtype=u.dtype)
-    dz = None
-    if z is not None:
-        dz = dz_out if dz_out is not None else torch.empty((Bsz, ndir, dim, Lp), device=dev, dtype=u.dtype)
-    dBC_part = torch.empty((Bsz, ndir, ngroups, 2 * N, Lp), device=dev, dtype=torch.float32)
+    G, ngroups, _ = _lib.scan_plan(L, dim, Bsz * ndir, True)
+    du = per_dir(Bsz, L, ndir, dim, dev, u.dtype)
+    ddelta = per_dir(Bsz, L, ndir, dim, dev, u.dtype)
+    dz = per_dir(Bsz, L, ndir, dim, dev, u.dtype) if z is not None else None
+    dbc_part = torch.empty((Bsz, ngroups, L, ndir, 2 * N), device=dev, dtype=torch.float32)
     dA_part = torch.empty((Bsz * ndir, dim, N), device=dev, dtype=torch.float32)
     dD_part = torch.empty((Bsz * ndir, dim), device=dev, dtype=torch.float32) if D is not None else None
     db_part = torch.empty((Bsz * ndir, dim), device=dev, dtype=torch.float32) if delta_bias is not None else None
 
-    d = _fill_desc(u, delta, A, Bm, Cm, D, z, delta_bias, softplus, seqlen, plan)
+    d = _fill_desc(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus, dtr_padded, G)
+    if dout.dtype != u.dtype:
+        raise TypeError("dout must have u's dtype")
     d.dout = _ptr(dout)
-    d.out_bs, d.out_ds, d.out_rs = _s3(dout)
-    d.ckpt = _ptr(ckpt)
-    d.ypre = _ptr(ypre)
-    if ypre is not None:
-        d.ypre_bs, d.ypre_ds, d.ypre_rs = _s3(ypre)
+    d.dout_bs, d.dout_ds, d.dout_ts = _s3(dout)
+    d.ckpt, d.ypre = _ptr(ckpt), _ptr(ypre)
+    d.out_bs, d.out_ds, d.out_ts = _s3(du)
+    if ypre is not None and _s3(ypre) != _s3(du):
+        raise ValueError("ypre must have the (B, L, ndir, dim) storage the forward wrote")
     d.du, d.ddelta, d.dz = _ptr(du), _ptr(ddelta), _ptr(dz)
-    if _s3(du) != _s3(u) or _s3(ddelta) != _s3(delta):
-        # du / ddelta are written with u's / delta's strides
-        raise ValueError("u and delta must be dense (B, ndir, dim, Lp) tensors for backward")
-    if dz is not None:
-        d.dz_bs, d.dz_ds, d.dz_rs = _s3(dz)
-    d.dBC_part, d.dA_part, d.dD_part, d.dbias_part = _ptr(dBC_part), _ptr(dA_part), _ptr(dD_part), _ptr(db_part)
-    d.dbc_rs = Lp
+    d.dbc_part, d.dA_part, d.dD_part, d.dbias_part = _ptr(dbc_part), _ptr(dA_part), _ptr(dD_part), _ptr(db_part)
     with _timed("scan_bwd"):
         _lib.check(lib.bimamba_selective_scan_bwd(C.byref(d), _stream()), "bimamba_selective_scan_bwd")
 
-    dBC = torch.empty((Bsz, ndir, 2 * N, Lp), device=dev, dtype=bc_out_dtype or Bm.dtype)
-    cols = 2 * N * Lp
-    reduce_raw(dBC_part, dBC, groups=Bsz * ndir, rows=ngroups, cols=cols, part_gs=ngroups * cols,
-               row_stride=cols, out_gs=cols)
+    dbc = per_dir(Bsz, L, ndir, 2 * N, dev, bc_out_dtype or u.dtype)
+    cols = L * ndir * 2 * N
+    reduce_raw(dbc_part, dbc, groups=Bsz, rows=ngroups, cols=cols, part_gs=ngroups * cols, row_stride=cols,
+               out_gs=cols)
     dA = torch.empty((dim, N), device=dev, dtype=torch.float32)
     reduce_raw(dA_part, dA, 1, Bsz * ndir, dim * N, 0, dim * N, 0)
     dD = dbias = None
@@ -211,12 +235,17 @@ def scan_bwd_raw(u, delta, A, Bm, Cm, D, z, delta_bias, softplus: bool, seqlen: 
     if delta_bias is not None:
         dbias = torch.empty((dim,), device=dev, dtype=torch.float32)
         reduce_raw(db_part, dbias, 1, Bsz * ndir, dim, 0, dim, 0)
-    return du, ddelta, dz, dBC, dA, dD, dbias
+    return du, ddelta, dz, dbc, dA, dD, dbias
 
 
 # ----------------------------------------------------------------------------------------
-# op-level autograd Functions (single direction, upstream signatures)
+# op-level autograd Functions (single direction, upstream signatures, (B, D, L) operands)
 # ----------------------------------------------------------------------------------------
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    """(B, C, L) -> contiguous channel-last (B, L, C)."""
+    return t.transpose(1, 2).contiguous()
+
+
 class CausalConv1dFn(torch.autograd.Function):
     """causal_conv1d_fn: x (B, D, L), weight (D, K), bias (D) -> (B, D, L).  mamba_block.py:52-55."""
 
@@ -226,31 +255,28 @@ class CausalConv1dFn(torch.autograd.Function):
             raise NotImplementedError("activation must be None, silu, or swish")
         _require_cuda(x, weight, bias)
         silu = activation is not None
-        if x.stride(2) != 1:
-            x = x.contiguous()
+        xl = _cl(x)
         w32, b32 = _f32c(weight), _f32c(bias)
-        Bsz, D, L = x.shape
-        out = torch.empty((Bsz, D, L), device=x.device, dtype=x.dtype)
-        conv_fwd_raw(x, w32, b32, out.unsqueeze(1), L, silu)
-        ctx.save_for_backward(x, w32, b32 if b32 is not None else torch.empty(0))
+        Bsz, L, D = xl.shape
+        out = torch.empty((Bsz, L, D), device=x.device, dtype=x.dtype)
+        conv_fwd_raw(xl, w32, b32, out.unsqueeze(1), silu)
+        ctx.save_for_backward(xl, w32, b32 if b32 is not None else torch.empty(0))
         ctx.silu, ctx.has_bias = silu, bias is not None
         ctx.wdtype = weight.dtype
         ctx.bdtype = bias.dtype if bias is not None else None
-        return out
+        return out.transpose(1, 2)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w32, b32 = ctx.saved_tensors
+        xl, w32, b32 = ctx.saved_tensors
         b32 = b32 if ctx.has_bias else None
-        dout = dout.to(x.dtype)
-        if dout.stride(2) != 1:
-            dout = dout.contiguous()
-        dx = torch.empty_like(x, memory_format=torch.contiguous_format)
-        dwb = conv_bwd_raw(x, w32, b32, dout.unsqueeze(1), dx, x.shape[2], ctx.silu)
+        gl = _cl(dout.to(xl.dtype))
+        dx = torch.empty_like(xl)
+        dwb = conv_bwd_raw(xl, w32, b32, gl.unsqueeze(1), dx, ctx.silu)
         K = w32.shape[1]
         dw = dwb[:, :K].to(ctx.wdtype)
         db = dwb[:, K].to(ctx.bdtype) if ctx.has_bias else None
-        return dx, dw, db, None
+        return dx.transpose(1, 2), dw, db, None
 
 
 def causal_conv1d_fn(x, weight, bias=None, seq_idx=None, initial_states=None, return_final_states=False,
@@ -281,46 +307,40 @@ class SelectiveScanFn(torch.autograd.Function):
         Bm, Cm = _as_bnl(B, "B"), _as_bnl(C, "C")
         if A.shape[1] != D_STATE:
             raise NotImplementedError("d_state must be 16 (the Phase-6 configuration)")
-        u = u.contiguous()
-        delta = delta.to(u.dtype).contiguous()
-        zc = z.to(u.dtype).contiguous() if z is not None else None
-        Bm = Bm.contiguous()
-        Cm = Cm.to(Bm.dtype).contiguous()
+        io = u.dtype
+        ul = _cl(u).unsqueeze(1)
+        dl = _cl(delta.to(io)).unsqueeze(1)
+        zl = _cl(z.to(io)).unsqueeze(1) if z is not None else None
+        bc = torch.cat([Bm.to(io).transpose(1, 2), Cm.to(io).transpose(1, 2)], dim=2).unsqueeze(1)   # (B, 1, L, 32)
         A32, D32, b32 = _f32c(A), _f32c(D), _f32c(delta_bias)
-        L = u.shape[2]
         needs_bwd = any(t is not None and t.requires_grad for t in (u, delta, A, B, C, D, z, delta_bias))
-        out, ckpt, ypre, plan = scan_fwd_raw(u.unsqueeze(1), delta.unsqueeze(1), A32, Bm.unsqueeze(1),
-                                             Cm.unsqueeze(1), D32, None if zc is None else zc.unsqueeze(1), b32,
-                                             bool(delta_softplus), L, needs_bwd)
-        ctx.save_for_backward(u, delta, A32, Bm, Cm, D32 if D32 is not None else torch.empty(0),
-                              zc if zc is not None else torch.empty(0), b32 if b32 is not None else torch.empty(0),
+        out, ckpt, ypre = scan_fwd_raw(ul, zl, dl, bc, None, None, A32, D32, b32, bool(delta_softplus), needs_bwd)
+        ctx.save_for_backward(ul, dl, A32, bc, D32 if D32 is not None else torch.empty(0),
+                              zl if zl is not None else torch.empty(0), b32 if b32 is not None else torch.empty(0),
                               ckpt if ckpt is not None else torch.empty(0),
                               ypre if ypre is not None else torch.empty(0))
-        ctx.meta = (D is not None, z is not None, delta_bias is not None, bool(delta_softplus), plan,
+        ctx.meta = (D is not None, z is not None, delta_bias is not None, bool(delta_softplus),
                     A.dtype, None if D is None else D.dtype, None if delta_bias is None else delta_bias.dtype,
-                    B.dtype, C.dtype, Bshape, Cshape, None if z is None else z.dtype)
-        return out[:, 0]
+                    B.dtype, C.dtype, Bshape, Cshape, None if z is None else z.dtype, delta.dtype)
+        return out[:, 0].transpose(1, 2)
 
     @staticmethod
     def backward(ctx, dout):
-        u, delta, A32, Bm, Cm, D32, zc, b32, ckpt, ypre = ctx.saved_tensors
-        (hasD, hasz, hasb, softplus, plan, Adt, Ddt, bdt, Bdt, Cdt, Bshape, Cshape, zdt) = ctx.meta
+        ul, dl, A32, bc, D32, zl, b32, ckpt, ypre = ctx.saved_tensors
+        (hasD, hasz, hasb, softplus, Adt, Ddt, bdt, Bdt, Cdt, Bshape, Cshape, zdt, deltadt) = ctx.meta
         D32 = D32 if hasD else None
-        zc = zc if hasz else None
+        zl = zl if hasz else None
         b32 = b32 if hasb else None
         ckpt = ckpt if ckpt.numel() else None
         ypre = ypre if ypre.numel() else None
-        dout = dout.to(u.dtype).contiguous()
-        L = u.shape[2]
-        du, ddelta, dz, dBC, dA, dD, dbias = scan_bwd_raw(
-            u.unsqueeze(1), delta.unsqueeze(1), A32, Bm.unsqueeze(1), Cm.unsqueeze(1), D32,
-            None if zc is None else zc.unsqueeze(1), b32, softplus, L, dout.unsqueeze(1), ckpt, ypre, plan,
-            bc_out_dtype=torch.float32)
+        gl = _cl(dout.to(ul.dtype)).unsqueeze(1)
+        du, ddelta, dz, dbc, dA, dD, dbias = scan_bwd_raw(
+            ul, zl, dl, bc, None, None, A32, D32, b32, softplus, gl, ckpt, ypre, bc_out_dtype=torch.float32)
         N = A32.shape[1]
-        dB = dBC[:, 0, :N].to(Bdt).reshape(Bshape)
-        dC = dBC[:, 0, N:].to(Cdt).reshape(Cshape)
-        return (du[:, 0], ddelta[:, 0], dA.to(Adt), dB, dC,
-                dD.to(Ddt) if hasD else None, dz[:, 0].to(zdt) if hasz else None,
+        dB = dbc[:, 0, :, :N].transpose(1, 2).to(Bdt).reshape(Bshape)
+        dC = dbc[:, 0, :, N:].transpose(1, 2).to(Cdt).reshape(Cshape)
+        return (du[:, 0].transpose(1, 2), ddelta[:, 0].transpose(1, 2).to(deltadt), dA.to(Adt), dB, dC,
+                dD.to(Ddt) if hasD else None, dz[:, 0].transpose(1, 2).to(zdt) if hasz else None,
                 dbias.to(bdt) if hasb else None, None)
 
 
@@ -334,14 +354,30 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
 # ----------------------------------------------------------------------------------------
 # the fused block: both directions, shared weights
 # ----------------------------------------------------------------------------------------
+def pack_x_proj(W_x: torch.Tensor, R: int, N: int, dtype) -> torch.Tensor:
+    """x_proj.weight (R + 2N, D) -> (48, D): rows [B | C | dt_r | 0] so one GEMM emits the row layout the
+    scan kernels stage with aligned vector copies (mamba_block.py:73-75 splits [dt_r | B | C])."""
+    D = W_x.shape[1]
+    Wp = torch.zeros((XW, D), device=W_x.device, dtype=dtype)
+    Wp[:N] = W_x[R:R + N]
+    Wp[N:2 * N] = W_x[R + N:R + 2 * N]
+    Wp[2 * N:2 * N + R] = W_x[:R]
+    return Wp
+
+
+def unpack_x_proj_grad(dWp: torch.Tensor, R: int, N: int) -> torch.Tensor:
+    return torch.cat([dWp[2 * N:2 * N + R], dWp[:N], dWp[N:2 * N]], dim=0)
+
+
 class BiMambaInnerFn(torch.autograd.Function):
     """out = M(x) [+ flip(M(flip(x)))] for one Mamba block M with shared weights.
 
     Reference: mamba_block.py:41-63 for M, DualStreamSEMamba.py:473-481 for the two directions.
     Uses: in_proj(flip x) = flip(in_proj x) so xz is computed once; the reverse
-    direction reads the same x, z back to front; out_proj is applied once to y_fwd + y_rev.
-    GEMMs are library calls in this version (cuBLAS through torch.matmul); conv, scan and all
-    reductions are this repository's CUDA kernels.
+    direction reads the same x, z back to front; out_proj is ONE GEMM over [y_fwd | y_rev] against
+    [W_out | W_out].  The dt projection (K = 9) is fused into the scan kernels.
+    GEMMs are library calls in this version (cuBLAS through torch.matmul); conv, scan, dt_proj and
+    all reductions are this repository's CUDA kernels.
     """
 
     @staticmethod
@@ -354,81 +390,88 @@ class BiMambaInnerFn(torch.autograd.Function):
             R = W_dt.shape[1]
             if N != D_STATE:
                 raise NotImplementedError("d_state must be 16 (the Phase-6 configuration)")
+            if R > MAX_DT_RANK:
+                raise NotImplementedError("dt_rank must be <= 16")
             ndir = 2 if bidirectional else 1
-            Lp = round_up(max(L, 1), 8)
+            M = Bsz * L
             dev = x.device
-            Wi, Wx, Wd, Wo = (w.detach().to(cdtype) for w in (W_in, W_x, W_dt, W_out))
+            Wi = W_in.detach().to(cdtype)
+            Wxp = pack_x_proj(W_x.detach(), R, N, cdtype)
+            Wo = W_out.detach().to(cdtype)
+            Wo2 = torch.cat([Wo] * ndir, dim=1) if ndir > 1 else Wo           # (dm, ndir*D)
+            Wd32 = _f32c(W_dt)
             cw32 = _f32c(conv_w).reshape(D, -1)
             cb32 = _f32c(conv_b)
             A32 = -torch.exp(A_log.detach().float())
             D32, bdt32 = _f32c(Dp), _f32c(b_dt)
 
-            x_pad = torch.zeros((Bsz, Lp, dm), device=dev, dtype=cdtype)
-            x_pad[:, :L] = x.detach()
-            xz = torch.matmul(Wi, x_pad.transpose(1, 2))                      # (B, 2D, Lp)   mamba_block.py:48
-            xs, z = xz[:, :D], xz[:, D:]                                      # :49 (views)
-            xc = torch.empty((Bsz, ndir, D, Lp), device=dev, dtype=cdtype)
-            conv_fwd_raw(xs, cw32, cb32, xc, L, True)                         # :52-55, both directions
-            x_dbl = torch.matmul(Wx, xc)                                      # (B, ndir, R+2N, Lp)   :73
-            delta = torch.matmul(Wd, x_dbl[:, :, :R])                         # (B, ndir, D, Lp)      :80 (pre-bias)
+            x2 = x.detach().to(cdtype).reshape(M, dm)
+            xz = torch.mm(x2, Wi.t())                                         # (M, 2D)   mamba_block.py:48
+            xz3 = xz.view(Bsz, L, 2 * D)
+            xs, z = xz3[:, :, :D], xz3[:, :, D:]                              # :49 (views)
+            xc = per_dir(Bsz, L, ndir, D, dev, cdtype)
+            conv_fwd_raw(xs, cw32, cb32, xc, True)                            # :52-55, both directions
+            xdbl = torch.mm(rows2d(xc), Wxp.t())                              # (M*ndir, 48)   :73
+            xd4 = xdbl.view(Bsz, L, ndir, XW).permute(0, 2, 1, 3)
             needs_bwd = any(ctx.needs_input_grad)
-            y, ckpt, ypre, plan = scan_fwd_raw(xc, delta, A32, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], D32,
-                                               z.unsqueeze(1), bdt32, True, L, needs_bwd)   # :82-120, :61
-            ysum = y[:, 0] + y[:, 1] if ndir == 2 else y[:, 0]                # DualStreamSEMamba.py:481 (before out_proj)
-            out = torch.matmul(ysum.transpose(1, 2)[:, :L], Wo.t())           # (B, L, dm)   mamba_block.py:62
+            y, ckpt, ypre = scan_fwd_raw(xc, z.unsqueeze(1).expand(Bsz, ndir, L, D), None, xd4[..., :2 * N],
+                                         xd4[..., 2 * N:], Wd32, A32, D32, bdt32, True, needs_bwd,
+                                         dtr_padded=True)                     # :80-120, :61
+            out = torch.mm(rows2d(y).view(M, ndir * D), Wo2.t()).view(Bsz, L, dm)   # :62 + DualStreamSEMamba.py:481
             if needs_bwd:
-                ctx.save_for_backward(x_pad, xz, xc, x_dbl, delta, ysum, Wi, Wx, Wd, Wo, cw32, cb32, A32, D32, bdt32,
+                ctx.save_for_backward(x2, xz, xc, xdbl, y, Wi, Wxp, Wd32, Wo, cw32, cb32, A32, D32, bdt32,
                                       ckpt if ckpt is not None else torch.empty(0), ypre)
-                ctx.meta = (L, ndir, plan, x.dtype,
+                ctx.meta = (Bsz, L, ndir, R, x.dtype,
                             tuple(t.dtype for t in (W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out)),
                             tuple(conv_w.shape))
             return out
 
     @staticmethod
     def backward(ctx, dout):
-        (x_pad, xz, xc, x_dbl, delta, ysum, Wi, Wx, Wd, Wo, cw32, cb32, A32, D32, bdt32, ckpt, ypre) = ctx.saved_tensors
-        L, ndir, plan, xdt, pdt, cw_shape = ctx.meta
+        (x2, xz, xc, xdbl, y, Wi, Wxp, Wd32, Wo, cw32, cb32, A32, D32, bdt32, ckpt, ypre) = ctx.saved_tensors
+        Bsz, L, ndir, R, xdt, pdt, cw_shape = ctx.meta
         ckpt = ckpt if ckpt.numel() else None
         with torch.autocast("cuda", enabled=False):
             cd = xz.dtype
-            Bsz, Lp, dm = x_pad.shape
+            M, dm = x2.shape
             D = xz.shape[1] // 2
             N = A32.shape[1]
-            R = Wd.shape[1]
-            dev = xz.device
-            xs, z = xz[:, :D], xz[:, D:]
+            xz3 = xz.view(Bsz, L, 2 * D)
+            xs, z = xz3[:, :, :D], xz3[:, :, D:]
+            xd4 = xdbl.view(Bsz, L, ndir, XW).permute(0, 2, 1, 3)
 
-            dout_pad = torch.zeros((Bsz, Lp, dm), device=dev, dtype=cd)
-            dout_pad[:, :L] = dout
+            g2 = dout.to(cd).reshape(M, dm)
             # out_proj
-            dy = torch.matmul(Wo.t(), dout_pad.transpose(1, 2))               # (B, D, Lp), shared by both directions
-            dW_out = torch.bmm(dout_pad.transpose(1, 2), ysum.transpose(1, 2)).sum(0)   # (dm, D)
-            # scan (both directions in one launch); dy is broadcast over the direction axis
-            dxz = torch.empty_like(xz)
-            dz2 = torch.empty((Bsz, ndir, D, Lp), device=dev, dtype=cd)
-            dyb = dy.unsqueeze(1).expand(Bsz, ndir, D, Lp)
-            du, ddelta, dz2, dBC, dA, dD, dbdt = scan_bwd_raw(
-                xc, delta, A32, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], D32, z.unsqueeze(1), bdt32, True, L,
-                dyb, ckpt, ypre, plan, dz_out=dz2, bc_out_dtype=cd)
-            if ndir == 2:
-                torch.add(dz2[:, 0], dz2[:, 1], out=dxz[:, D:])
-            else:
-                dxz[:, D:].copy_(dz2[:, 0])
-            # dt_proj
-            ddtr = torch.matmul(Wd.t(), ddelta)                               # (B, ndir, R, Lp)
-            dW_dt = torch.bmm(ddelta.flatten(0, 1), x_dbl[:, :, :R].flatten(0, 1).transpose(1, 2)).sum(0)   # (D, R)
+            dy = torch.mm(g2, Wo)                                             # (M, D), shared by both directions
+            y2 = rows2d(y).view(M, ndir * D)
+            dW_out2 = torch.mm(g2.t(), y2)                                    # (dm, ndir*D)
+            dW_out = dW_out2[:, :D] + dW_out2[:, D:] if ndir > 1 else dW_out2
+            # scan (both directions in one launch); dy and z are broadcast over the direction axis
+            dyb = dy.view(Bsz, 1, L, D).expand(Bsz, ndir, L, D)
+            du, ddelta, dz, dbc, dA, dD, dbdt = scan_bwd_raw(
+                xc, z.unsqueeze(1).expand(Bsz, ndir, L, D), None, xd4[..., :2 * N], xd4[..., 2 * N:], Wd32,
+                A32, D32, bdt32, True, dyb, ckpt, ypre, dtr_padded=True)
+            # dt_proj (weight gradient in fp32; the data gradient joins the x_proj row)
+            dd2 = rows2d(ddelta)                                              # (M*ndir, D)
+            Wd_pad = torch.zeros((D, XW - 2 * N), device=dd2.device, dtype=cd)
+            Wd_pad[:, :R] = Wd32
+            dxdbl = torch.cat([rows2d(dbc), torch.mm(dd2, Wd_pad)], dim=1)    # (M*ndir, 48) [dB | dC | ddt_r | 0]
+            dW_dt = torch.mm(dd2.t(), xdbl[:, 2 * N:2 * N + R])               # (D, R)
             # x_proj
-            dxdbl = torch.cat([ddtr, dBC], dim=2)                             # (B, ndir, R+2N, Lp)
-            dW_x = torch.bmm(dxdbl.flatten(0, 1), xc.flatten(0, 1).transpose(1, 2)).sum(0)                  # (R+2N, D)
-            dxc = torch.baddbmm(du.flatten(0, 1), Wx.t().unsqueeze(0).expand(Bsz * ndir, D, R + 2 * N),
-                                dxdbl.flatten(0, 1)).view(Bsz, ndir, D, Lp)
-            # conv (writes dx into the x half of dxz)
-            dwb = conv_bwd_raw(xs, cw32, cb32, dxc, dxz[:, :D], L, True)
+            xc2 = rows2d(xc)
+            dW_xp = torch.mm(dxdbl.t(), xc2)                                  # (48, D)
+            dxc = torch.addmm(rows2d(du), dxdbl, Wxp)                         # (M*ndir, D)
+            dxc4 = dxc.view(Bsz, L, ndir, D).permute(0, 2, 1, 3)
+            # conv (writes dx into the x half and dz_fwd + dz_rev into the z half of dxz)
+            dxz = torch.empty_like(xz)
+            dxz3 = dxz.view(Bsz, L, 2 * D)
+            dwb = conv_bwd_raw(xs, cw32, cb32, dxc4, dxz3[:, :, :D], True, dz_in=dz, dz_out=dxz3[:, :, D:])
             K = cw32.shape[1]
             # in_proj
-            dW_in = torch.bmm(dxz, x_pad).sum(0)                              # (2D, dm)
-            dx = torch.matmul(dxz.transpose(1, 2)[:, :L], Wi)                 # (B, L, dm)
+            dW_in = torch.mm(dxz.t(), x2)                                     # (2D, dm)
+            dx = torch.mm(dxz, Wi).view(Bsz, L, dm)
             dA_log = dA * A32                                                 # A = -exp(A_log)
+            dW_x = unpack_x_proj_grad(dW_xp, R, N)
         return (dx.to(xdt), dW_in.to(pdt[0]), dwb[:, :K].reshape(cw_shape).to(pdt[1]), dwb[:, K].to(pdt[2]),
                 dW_x.to(pdt[3]), dW_dt.to(pdt[4]), dbdt.to(pdt[5]), dA_log.to(pdt[6]), dD.to(pdt[7]),
                 dW_out.to(pdt[8]), None, None)
