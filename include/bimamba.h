@@ -150,6 +150,21 @@ int bimamba_reduce_partials(const float* part, void* out, int64_t groups, int64_
                             int64_t part_gs, int64_t row_stride, int64_t out_gs,
                             int out_dtype, int accumulate, bimamba_stream_t stream);
 
+/* LayerNorm over the channel axis of a dense (rows, channels) matrix: the nn.LayerNorm(d_model) calls
+ * of PN_BiMambas_Encoder (DualStreamSEMamba.py:458-459, :472, :482) and norm_f (:703, :759).
+ * y = (x - mean) * rstd * gamma + beta, written in out_dtype (the dtype the following GEMM reads).
+ * mean / rstd (rows) fp32 are saved for the backward (may be NULL for inference).  channels <= 1024. */
+int bimamba_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                          float* rstd, int64_t rows, int channels, float eps, int in_dtype, int out_dtype,
+                          bimamba_stream_t stream);
+
+/* dx (x's dtype) and per-CTA partials dgb_part (nblocks, 2, channels) fp32 = [dgamma | dbeta] with
+ * nblocks = bimamba_layernorm_bwd_blocks(rows); reduce with bimamba_reduce_partials.  channels <= 256. */
+int bimamba_layernorm_bwd_blocks(int64_t rows);
+int bimamba_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean,
+                          const float* rstd, void* dx, float* dgb_part, int64_t rows, int channels,
+                          int x_dtype, int dy_dtype, bimamba_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

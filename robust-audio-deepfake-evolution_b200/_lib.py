@@ -22,7 +22,7 @@ EXPORTS = (
     "bimamba_abi_version", "bimamba_last_error", "bimamba_scan_plan",
     "bimamba_selective_scan_fwd", "bimamba_selective_scan_bwd",
     "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_conv_bwd_slices",
-    "bimamba_reduce_partials",
+    "bimamba_reduce_partials", "bimamba_layernorm_fwd", "bimamba_layernorm_bwd_blocks", "bimamba_layernorm_bwd",
 )
 
 
@@ -88,6 +88,13 @@ def load() -> C.CDLL:
         lib.bimamba_conv_bwd_slices.argtypes = [i32, i32]
         lib.bimamba_reduce_partials.restype = i32
         lib.bimamba_reduce_partials.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp]
+        f32 = C.c_float
+        lib.bimamba_layernorm_fwd.restype = i32
+        lib.bimamba_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, i32, vp]
+        lib.bimamba_layernorm_bwd_blocks.restype = i32
+        lib.bimamba_layernorm_bwd_blocks.argtypes = [i64]
+        lib.bimamba_layernorm_bwd.restype = i32
+        lib.bimamba_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]
         got = lib.bimamba_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError(f"libbimamba ABI {got} != expected {ABI_VERSION}; rebuild the library")

@@ -62,11 +62,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // softplus with the reference's threshold (torch.nn.functional.softplus: x if x > 20).
 // log1p(e) for small e is taken as e - e^2/2 + e^3/3 (lg2(1+e) would lose e's low bits).
+// Branch-free (lanes of a warp mix both ranges).
 __device__ __forceinline__ float softplus_f(float v) {
-  if (v > 20.f) return v;
-  const float e = ex2_approx(v * kLog2e);
-  if (e < 0.03125f) return e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.f);
-  return lg2_approx(1.f + e) * kLn2;
+  const float e = ex2_approx(fminf(v, 20.f) * kLog2e);
+  const float small = e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.f);
+  const float big = lg2_approx(1.f + e) * kLn2;
+  const float r = e < 0.03125f ? small : big;
+  return v > 20.f ? v : r;
 }
 
 __device__ __forceinline__ float sigmoid_f(float v) { return rcp_approx(1.f + ex2_approx(-v * kLog2e)); }

@@ -261,17 +261,36 @@ conv_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const floa
 }
 
 // out[g*out_gs + j] (+)= sum_i part[g*part_gs + i*row_stride + j]
+// Block = (256 / RL columns) x (RL row lanes); row lane r sums rows r, r+RL, ... in order and the
+// lanes are combined in order through shared memory, so the result does not depend on timing.
+template <int RL>
 __global__ void __launch_bounds__(256)
 reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t groups, int64_t rows, int64_t cols,
               int64_t part_gs, int64_t row_stride, int64_t out_gs, int dt, int accumulate) {
-  const int64_t total = groups * cols;
-  for (int64_t gid = (int64_t)blockIdx.x * 256 + threadIdx.x; gid < total; gid += (int64_t)gridDim.x * 256) {
-    const int64_t g = gid / cols, j = gid - g * cols;
-    const float* src = part + g * part_gs + j;
+  constexpr int CPB = 256 / RL;
+  __shared__ float sm[RL][CPB + 1];
+  const int cx = threadIdx.x % CPB, ry = threadIdx.x / CPB;
+  const int64_t tiles = (cols + CPB - 1) / CPB;
+  for (int64_t bid = blockIdx.x; bid < groups * tiles; bid += gridDim.x) {
+    const int64_t g = bid / tiles, j = (bid - g * tiles) * CPB + cx;
     float s = 0.f;
-    for (int64_t i = 0; i < rows; ++i) s += __ldg(src + i * row_stride);
-    if (accumulate) s += ld_f(out, g * out_gs + j, dt);
-    st_f(out, g * out_gs + j, s, dt);
+    if (j < cols) {
+      const float* src = part + g * part_gs + j;
+      for (int64_t i = ry; i < rows; i += RL) s += __ldg(src + i * row_stride);
+    }
+    if (RL > 1) {
+      sm[ry][cx] = s;
+      __syncthreads();
+      if (ry == 0) {
+#pragma unroll
+        for (int r = 1; r < RL; ++r) s += sm[r][cx];
+      }
+    }
+    if (ry == 0 && j < cols) {
+      if (accumulate) s += ld_f(out, g * out_gs + j, dt);
+      st_f(out, g * out_gs + j, s, dt);
+    }
+    if (RL > 1) __syncthreads();
   }
 }
 
@@ -382,11 +401,17 @@ extern "C" int bimamba_reduce_partials(const float* part, void* out, int64_t gro
   if (groups * cols == 0) return 0;
   if (!part || !out) { set_err("reduce: null operand"); return -1; }
   if (out_dtype < 0 || out_dtype > 2 || groups < 0 || rows < 0 || cols < 0) { set_err("reduce: bad sizes"); return -2; }
-  const int64_t total = groups * cols;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
+  auto nblocks = [&](int cpb) {
+    int64_t n = groups * ((cols + cpb - 1) / cpb);
+    return (unsigned)(n > 148 * 64 ? 148 * 64 : n);
+  };
+  if (rows <= 16)
+    reduce_kernel<1><<<nblocks(256), 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
+  else if (rows <= 96)
+    reduce_kernel<8><<<nblocks(32), 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
+  else
+    reduce_kernel<32><<<nblocks(8), 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

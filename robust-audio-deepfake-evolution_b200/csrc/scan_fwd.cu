@@ -29,28 +29,28 @@ namespace bimamba {
 
 constexpr int kFwdMaxThreads = 128;
 
-template <typename T>
+// kMode: 0 = delta given; 1 = fused dt projection with dt_rank <= 12; 2 = dt_rank <= 16.
+template <typename T, int kMode, bool kGate>
 __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_scan_desc p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool expl = kMode == 0;
+  constexpr int R4 = kMode == 1 ? 3 : 4;
   const int G = blockDim.x, tid = threadIdx.x;
   const int b = blockIdx.z, dir = blockIdx.y, d0 = blockIdx.x * G, d = d0 + tid;
   const bool ok = d < p.dim;
   const int L = p.seqlen, nck = (L + kT - 1) / kT;
-  const bool has_z = p.z != nullptr, expl = p.delta != nullptr;
   const bool softplus = (p.flags & BIMAMBA_FLAG_SOFTPLUS) != 0;
   const int R = expl ? 0 : p.dt_rank;
 
   const T* gu = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_bs + (int64_t)dir * p.u_ds;
-  const T* gz = has_z ? reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_bs + (int64_t)dir * p.z_ds : nullptr;
+  const T* gz = kGate ? reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_bs + (int64_t)dir * p.z_ds : nullptr;
   const T* gd = expl ? reinterpret_cast<const T*>(p.delta) + (int64_t)b * p.delta_bs + (int64_t)dir * p.delta_ds : nullptr;
   const T* gbc = reinterpret_cast<const T*>(p.bc) + (int64_t)b * p.bc_bs + (int64_t)dir * p.bc_ds;
-  const T* gdtr = R ? reinterpret_cast<const T*>(p.dtr) + (int64_t)b * p.dtr_bs + (int64_t)dir * p.dtr_ds : nullptr;
+  const T* gdtr = expl ? nullptr : reinterpret_cast<const T*>(p.dtr) + (int64_t)b * p.dtr_bs + (int64_t)dir * p.dtr_ds;
   const int64_t obase = (int64_t)b * p.out_bs + (int64_t)dir * p.out_ds;
-  T* gout = reinterpret_cast<T*>(p.out) + obase;
-  T* gyp = p.ypre ? reinterpret_cast<T*>(p.ypre) + obase : nullptr;
 
   // shared memory: [2][nact][kT*G] T | [2][kT*kXW] T | [kT*kXW] float
-  const int nact = 1 + (has_z ? 1 : 0) + (expl ? 1 : 0);
+  constexpr int nact = 1 + (kGate ? 1 : 0) + (expl ? 1 : 0);
   T* s_act = reinterpret_cast<T*>(smem_raw);
   T* s_xr = s_act + 2 * nact * kT * G;
   float* s_xf = reinterpret_cast<float*>(s_xr + 2 * kT * kXW);
@@ -58,10 +58,10 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
   constexpr int kV = 16 / sizeof(T);
   const bool dim_vec = (p.dim % kV) == 0;
   const bool vec_u = dim_vec && aligned16(gu + d0) && (p.u_ts % kV) == 0;
-  const bool vec_z = has_z && dim_vec && aligned16(gz + d0) && (p.z_ts % kV) == 0;
+  const bool vec_z = kGate && dim_vec && aligned16(gz + d0) && (p.z_ts % kV) == 0;
   const bool vec_d = expl && dim_vec && aligned16(gd + d0) && (p.delta_ts % kV) == 0;
   const bool vec_bc = aligned16(gbc) && (p.bc_ts % kV) == 0;
-  const bool vec_dtr = R && (p.flags & BIMAMBA_FLAG_DTR_PADDED) && aligned16(gdtr) && (p.dtr_ts % kV) == 0;
+  const bool vec_dtr = !expl && (p.flags & BIMAMBA_FLAG_DTR_PADDED) && aligned16(gdtr) && (p.dtr_ts % kV) == 0;
 
   auto stage = [&](int c0, int bf) {
     auto row_of = [&](int i) -> int64_t {
@@ -70,12 +70,11 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
     };
     T* sa = s_act + bf * nact * kT * G;
     stage_tile(sa, G, gu, p.u_ts, kT, G, d0, p.dim, vec_u, row_of, tid, G);
-    int k = 1;
-    if (has_z) stage_tile(sa + (k++) * kT * G, G, gz, p.z_ts, kT, G, d0, p.dim, vec_z, row_of, tid, G);
-    if (expl) stage_tile(sa + k * kT * G, G, gd, p.delta_ts, kT, G, d0, p.dim, vec_d, row_of, tid, G);
+    if (kGate) stage_tile(sa + kT * G, G, gz, p.z_ts, kT, G, d0, p.dim, vec_z, row_of, tid, G);
+    if (expl) stage_tile(sa + (nact - 1) * kT * G, G, gd, p.delta_ts, kT, G, d0, p.dim, vec_d, row_of, tid, G);
     T* sx = s_xr + bf * kT * kXW;
     stage_tile(sx, kXW, gbc, p.bc_ts, kT, 2 * kN, 0, 2 * kN, vec_bc, row_of, tid, G);
-    if (R) {
+    if (!expl) {
       const int w = vec_dtr ? 16 : R;
       stage_tile(sx + 2 * kN, kXW, gdtr, p.dtr_ts, kT, w, 0, w, vec_dtr, row_of, tid, G);
     }
@@ -84,7 +83,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
 
   // per-channel constants
   float2 A2[kN / 2], h[kN / 2];
-  float4 wdt[4];
+  float2 wdt[2 * R4];
   float bias = 0.f, Dd = 0.f;
 #pragma unroll
   for (int j = 0; j < kN / 2; ++j) {
@@ -92,7 +91,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
     A2[j] = make_float2(0.f, 0.f);
   }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) wdt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < 2 * R4; ++q) wdt[q] = make_float2(0.f, 0.f);
   if (ok) {
 #pragma unroll
     for (int j = 0; j < kN / 2; ++j) {
@@ -101,14 +100,18 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
     }
     if (p.delta_bias) bias = __ldg(p.delta_bias + d);
     if (p.D) Dd = __ldg(p.D + d);
-    if (R) {
+    if (!expl) {
       float* w = reinterpret_cast<float*>(wdt);
 #pragma unroll
-      for (int r = 0; r < BIMAMBA_MAX_DT_RANK; ++r)
+      for (int r = 0; r < 4 * R4; ++r)
         if (r < R) w[r] = __ldg(p.Wdt + (int64_t)d * R + r);
     }
   }
-  const int R4 = (R + 3) >> 2;
+  // output walks: element (t, d) with t advancing by +-1 per step
+  const int64_t ostep = dir ? -p.out_ts : p.out_ts;
+  int64_t opos = obase + (int64_t)(dir ? (L - 1) : 0) * p.out_ts + d;
+  T* const gout = reinterpret_cast<T*>(p.out);
+  T* const gyp = reinterpret_cast<T*>(p.ypre);
 
   if (nck > 0) stage(0, 0);
   for (int c0 = 0; c0 < nck; ++c0) {
@@ -133,32 +136,28 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
         for (int q = 0; q < 4; ++q) ck[q] = make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y);
       }
       const T* su = s_act + bf * nact * kT * G + tid;
-      const T* sz = su + kT * G;
-      const T* sd = su + (has_z ? 2 : 1) * kT * G;
-      const int nsteps = min(kT, L - c0 * kT);
-#pragma unroll 4
-      for (int i = 0; i < nsteps; ++i) {
+      const int nvalid = L - c0 * kT;  // steps of this chunk that exist (>= 1)
+#pragma unroll 2
+      for (int i = 0; i < kT; ++i) {
         const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW);
         const float u = to_f(su[i * G]);
-        float draw = bias;
+        float draw;
         if (expl) {
-          draw += to_f(sd[i * G]);
+          draw = bias + to_f(su[((nact - 1) * kT + i) * G]);
         } else {
+          float2 acc0 = make_float2(bias, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q < R4) {
-              const float4 x = xr[8 + q];
-              draw = fmaf(wdt[q].x, x.x, draw);
-              draw = fmaf(wdt[q].y, x.y, draw);
-              draw = fmaf(wdt[q].z, x.z, draw);
-              draw = fmaf(wdt[q].w, x.w, draw);
-            }
+          for (int q = 0; q < R4; ++q) {
+            const float4 x = xr[8 + q];
+            acc0 = __ffma2_rn(wdt[2 * q], make_float2(x.x, x.y), acc0);
+            acc1 = __ffma2_rn(wdt[2 * q + 1], make_float2(x.z, x.w), acc1);
           }
+          draw = (acc0.x + acc0.y) + (acc1.x + acc1.y);
         }
         const float delta = softplus ? softplus_f(draw) : draw;
         const float du = delta * u;
         const float2 dd = make_float2(delta, delta), duu = make_float2(du, du);
-        float2 y2 = make_float2(0.f, 0.f);
+        float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 Bq = xr[q], Cq = xr[4 + q];
@@ -166,24 +165,25 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
             const float2 x = __fmul2_rn(dd, A2[2 * q]);
             const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
             h[2 * q] = __ffma2_rn(a, h[2 * q], __fmul2_rn(duu, make_float2(Bq.x, Bq.y)));
-            y2 = __ffma2_rn(make_float2(Cq.x, Cq.y), h[2 * q], y2);
+            ya = __ffma2_rn(make_float2(Cq.x, Cq.y), h[2 * q], ya);
           }
           {
             const float2 x = __fmul2_rn(dd, A2[2 * q + 1]);
             const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
             h[2 * q + 1] = __ffma2_rn(a, h[2 * q + 1], __fmul2_rn(duu, make_float2(Bq.z, Bq.w)));
-            y2 = __ffma2_rn(make_float2(Cq.z, Cq.w), h[2 * q + 1], y2);
+            yb = __ffma2_rn(make_float2(Cq.z, Cq.w), h[2 * q + 1], yb);
           }
         }
-        float y = fmaf(Dd, u, y2.x + y2.y);
-        const int tau = c0 * kT + i;
-        const int64_t o = (int64_t)(dir ? (L - 1 - tau) : tau) * p.out_ts + d;
-        if (gyp) gyp[o] = from_f<T>(y);
-        if (has_z) {
-          const float z = to_f(sz[i * G]);
-          y *= z * sigmoid_f(z);
+        float y = fmaf(Dd, u, (ya.x + ya.y) + (yb.x + yb.y));
+        if (i < nvalid) {
+          if (gyp) gyp[opos] = from_f<T>(y);
+          if (kGate) {
+            const float z = to_f(su[(kT + i) * G]);
+            y *= z * sigmoid_f(z);
+          }
+          gout[opos] = from_f<T>(y);
         }
-        gout[o] = from_f<T>(y);
+        opos += ostep;
       }
     }
   }
@@ -194,14 +194,29 @@ static size_t fwd_smem_bytes(int G, int esize, bool has_z, bool expl) {
   return (size_t)2 * nact * kT * G * esize + (size_t)2 * kT * kXW * esize + (size_t)kT * kXW * 4;
 }
 
-template <typename T>
-static int launch_fwd(const bimamba_scan_desc* d, cudaStream_t st) {
+template <typename T, int kMode, bool kGate>
+static void launch_fwd2(const bimamba_scan_desc* d, cudaStream_t st) {
   const int G = d->group_channels;
-  const size_t smem = fwd_smem_bytes(G, (int)sizeof(T), d->z != nullptr, d->delta != nullptr);
+  const size_t smem = fwd_smem_bytes(G, (int)sizeof(T), kGate, kMode == 0);
   dim3 grid((d->dim + G - 1) / G, d->ndir, d->batch);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(scan_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  scan_fwd_kernel<T><<<grid, G, smem, st>>>(*d);
-  return 0;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(scan_fwd_kernel<T, kMode, kGate>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  scan_fwd_kernel<T, kMode, kGate><<<grid, G, smem, st>>>(*d);
+}
+
+template <typename T>
+static void launch_fwd(const bimamba_scan_desc* d, cudaStream_t st) {
+  const bool gate = d->z != nullptr;
+  const int mode = d->delta ? 0 : (d->dt_rank <= 12 ? 1 : 2);
+  if (gate) {
+    if (mode == 0) launch_fwd2<T, 0, true>(d, st);
+    else if (mode == 1) launch_fwd2<T, 1, true>(d, st);
+    else launch_fwd2<T, 2, true>(d, st);
+  } else {
+    if (mode == 0) launch_fwd2<T, 0, false>(d, st);
+    else if (mode == 1) launch_fwd2<T, 1, false>(d, st);
+    else launch_fwd2<T, 2, false>(d, st);
+  }
 }
 
 int check_desc(const bimamba_scan_desc* d, bool bwd);  // api.cu

@@ -7,6 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .mamba_simple import Mamba
+from .ops import layer_norm_fn
 
 
 class PN_BiMambas_Encoder(nn.Module):
@@ -27,9 +28,9 @@ class PN_BiMambas_Encoder(nn.Module):
 
     def forward(self, x):
         residual = x
-        x_norm = self.norm1(x)                                   # :472
-        mamba_out = self.mamba.forward_bidirectional(x_norm)     # :473-481 in one fused pass
-        mamba_out = self.norm2(mamba_out)                        # :482
+        x_norm = layer_norm_fn(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)               # :472
+        mamba_out = self.mamba.forward_bidirectional(x_norm)                                         # :473-481 in one fused pass
+        mamba_out = layer_norm_fn(mamba_out, self.norm2.weight, self.norm2.bias, self.norm2.eps)    # :482
         ff_out = self.feed_forward(mamba_out)                    # :483
         return ff_out + residual                                 # :485
 
@@ -53,7 +54,9 @@ class BiMambaBackend(nn.Module):
         return f_fused
 
     def forward(self, f_fused):
-        f_fused = self.norm_f(self.forward_features(f_fused))                       # :759
+        f_fused = self.forward_features(f_fused)
+        f_fused = layer_norm_fn(f_fused, self.norm_f.weight, self.norm_f.bias, self.norm_f.eps,
+                                out_dtype=f_fused.dtype)                                             # :759
         attn = F.softmax(self.attention_pool(f_fused), dim=1)                       # :762
         features = torch.matmul(attn.transpose(1, 2), f_fused).squeeze(1)           # :763
         features = self.dropout(features)                                           # :764

@@ -352,6 +352,68 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
 
 
 # ----------------------------------------------------------------------------------------
+# LayerNorm of the encoder layer (DualStreamSEMamba.py:472, :482, :759)
+# ----------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x) over the last axis, written directly in `out_dtype` (the dtype the next GEMM
+    reads); statistics in fp32.  x (..., C) fp32 / bf16 / fp16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        _require_cuda(x, weight, bias)
+        lib = _lib.load()
+        C_ = x.shape[-1]
+        x2 = x.detach().reshape(-1, C_)
+        if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) != C_):
+            x2 = x2.contiguous()
+        rows = x2.shape[0]
+        w32, b32 = _f32c(weight), _f32c(bias)
+        y = torch.empty((rows, C_), device=x.device, dtype=out_dtype)
+        needs_bwd = any(ctx.needs_input_grad)
+        mean = torch.empty((rows,), device=x.device, dtype=torch.float32) if needs_bwd else None
+        rstd = torch.empty((rows,), device=x.device, dtype=torch.float32) if needs_bwd else None
+        with _timed("ln_fwd"):
+            _lib.check(lib.bimamba_layernorm_fwd(_ptr(x2), _ptr(w32), _ptr(b32), _ptr(y), _ptr(mean), _ptr(rstd),
+                                                 rows, C_, float(eps), _dt(x2), _dt(y), _stream()),
+                       "bimamba_layernorm_fwd")
+        if needs_bwd:
+            ctx.save_for_backward(x2, w32, mean, rstd)
+            ctx.meta = (x.shape, weight.dtype, bias.dtype)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w32, mean, rstd = ctx.saved_tensors
+        shape, wdt, bdt = ctx.meta
+        lib = _lib.load()
+        rows, C_ = x2.shape
+        g2 = dy.reshape(rows, C_)
+        if g2.dtype not in _DT or (g2.dtype != x2.dtype and g2.dtype != torch.float32 and x2.dtype != torch.float32):
+            g2 = g2.to(x2.dtype)
+        g2 = g2.contiguous()
+        dx = torch.empty_like(x2)
+        nb = lib.bimamba_layernorm_bwd_blocks(rows)
+        part = torch.empty((nb, 2, C_), device=x2.device, dtype=torch.float32)
+        with _timed("ln_bwd"):
+            _lib.check(lib.bimamba_layernorm_bwd(_ptr(x2), _ptr(g2), _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(dx),
+                                                 _ptr(part), rows, C_, _dt(x2), _dt(g2), _stream()),
+                       "bimamba_layernorm_bwd")
+        dgb = torch.empty((2, C_), device=x2.device, dtype=torch.float32)
+        if rows == 0:
+            dgb.zero_()
+        else:
+            reduce_raw(part, dgb, groups=1, rows=nb, cols=2 * C_, part_gs=0, row_stride=2 * C_, out_gs=0)
+        return dx.view(shape), dgb[0].to(wdt), dgb[1].to(bdt), None, None
+
+
+def layer_norm_fn(x, weight, bias, eps=1e-5, out_dtype=None):
+    """LayerNorm over the last axis; out_dtype defaults to the autocast dtype when autocast is on, else x.dtype."""
+    if out_dtype is None:
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    return LayerNormFn.apply(x, weight, bias, eps, out_dtype)
+
+
+# ----------------------------------------------------------------------------------------
 # the fused block: both directions, shared weights
 # ----------------------------------------------------------------------------------------
 def pack_x_proj(W_x: torch.Tensor, R: int, N: int, dtype) -> torch.Tensor:

@@ -155,3 +155,28 @@ def test_causal_conv1d_widths_no_bias(K):
     ref = orc.causal_conv1d_ref(x.double(), w.double(), None, "silu")
     out = bm.causal_conv1d_fn(x.cuda(), w.cuda(), None, activation="silu")
     assert rel(out, ref) < 1e-5
+
+
+# ---------------------------------------------------------------- layer norm
+@pytest.mark.parametrize("C", [144, 64, 250])
+@pytest.mark.parametrize("dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                             (torch.bfloat16, torch.bfloat16)])
+def test_layer_norm(C, dtype, out_dtype):
+    """nn.LayerNorm of PN_BiMambas_Encoder (DualStreamSEMamba.py:472, :482) against torch in fp64."""
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(5, 37, C, generator=g) * 2 + 0.5).to(dtype)
+    w = 1 + 0.2 * torch.randn(C, generator=g)
+    b = 0.3 * torch.randn(C, generator=g)
+    cot = torch.randn(5, 37, C, generator=g).to(out_dtype)
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5)
+    (ref * cot.double()).sum().backward()
+    xd, wd, bd = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    out = bm.ops.layer_norm_fn(xd, wd, bd, 1e-5, out_dtype=out_dtype)
+    assert out.dtype == out_dtype and out.shape == x.shape
+    out.backward(cot.cuda())
+    tol = 1e-5 if (dtype == torch.float32 and out_dtype == torch.float32) else 2e-2
+    assert rel(out, ref) < tol
+    assert rel(xd.grad, xr.grad) < tol
+    assert rel(wd.grad, wr.grad) < tol
+    assert rel(bd.grad, br.grad) < tol
