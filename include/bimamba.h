@@ -54,7 +54,8 @@ extern "C" {
 
 #define BIMAMBA_DSTATE 16       /* d_state of the Phase-6 configuration (Phase6_Proposed.conf:26) */
 #define BIMAMBA_MAX_DT_RANK 16
-#define BIMAMBA_CHUNK 16        /* steps per chunk = checkpoint interval */
+#define BIMAMBA_CHUNK 16        /* time steps staged per forward chunk */
+#define BIMAMBA_CKPT 8          /* checkpoint interval = steps per backward chunk */
 
 typedef void* bimamba_stream_t; /* a cudaStream_t */
 
@@ -82,8 +83,9 @@ typedef struct bimamba_scan_desc {
   void* out;         /* fwd: (batch, ndir, L, dim) gated output                          */
   void* ypre;        /* (batch, ndir, L, dim) y before the z gate, strides = out's.  Written by
                         fwd when non-NULL; read by bwd to form dz (required there with z) */
-  float* ckpt;       /* (batch, ndir, nchunks, dim, 16) fp32 state entering each 16-step chunk;
-                        written by fwd when non-NULL, read by bwd when nchunks > 1        */
+  float* ckpt;       /* (batch, ndir, nckpt, dim, 16) fp32 state entering every 8-step chunk,
+                        nckpt = ceil(L / 8); written by fwd when non-NULL, read by bwd
+                        (required there when nckpt > 1)                                   */
   /* backward only */
   const void* dout;  /* (batch, ndir, L, dim), strides dout_*                             */
   void* du;          /* (batch, ndir, L, dim), strides = out's (out_bs/out_ds/out_ts)     */
@@ -113,8 +115,8 @@ int bimamba_abi_version(void);
 const char* bimamba_last_error(void);
 
 /* Chooses the channel-group width for (seqlen, dim, batch*ndir); backward != 0 selects the
- * backward kernel's geometry.  Returns nchunks = ceil(seqlen / 16); *ngroups = CTAs per
- * (batch, dir) = ceil(dim / *group_channels). */
+ * backward kernel's geometry.  Returns nckpt = ceil(seqlen / 8), the number of checkpoints per
+ * (batch, dir, channel); *ngroups = CTAs per (batch, dir) = ceil(dim / *group_channels). */
 int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, int* group_channels, int* ngroups);
 
 int bimamba_selective_scan_fwd(const bimamba_scan_desc* d, bimamba_stream_t stream);

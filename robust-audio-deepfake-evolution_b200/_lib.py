@@ -114,4 +114,8 @@ def scan_plan(seqlen: int, dim: int, rows: int, backward: bool = False):
     """-> (group_channels, ngroups, nchunks)"""
     gc, ng = C.c_int(0), C.c_int(0)
     n = load().bimamba_scan_plan(int(seqlen), int(dim), int(rows), int(backward), C.byref(gc), C.byref(ng))
-    return gc.value, ng.value, n
+    g = gc.value
+    ov = os.environ.get("BIMAMBA_BWD_G" if backward else "BIMAMBA_FWD_G")   # tuning experiments only
+    if ov:
+        g = int(ov)
+    return g, (dim + g - 1) // g, n

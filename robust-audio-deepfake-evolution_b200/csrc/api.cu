@@ -24,7 +24,7 @@ int check_desc(const bimamba_scan_desc* d, bool bwd) {
   if (!bwd && !d->out) { set_err("null out"); return -7; }
   if (bwd) {
     if (!d->dout || !d->du || !d->ddelta || !d->dbc_part || !d->dA_part) { set_err("null backward operand"); return -8; }
-    if (d->seqlen > kT && !d->ckpt) { set_err("backward needs the forward checkpoints"); return -9; }
+    if (d->seqlen > BIMAMBA_CKPT && !d->ckpt) { set_err("backward needs the forward checkpoints"); return -9; }
     if (d->z && d->dz && !d->ypre) { set_err("gated backward needs ypre saved by the forward"); return -11; }
   }
   return 0;
@@ -40,9 +40,13 @@ extern "C" const char* bimamba_last_error(void) { return g_err; }
 extern "C" int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, int* group_channels, int* ngroups) {
   int G;
   if (backward) {
+    // 32 channels per pass; more passes per CTA amortise the dB/dC reduction, fewer fill the GPU
     G = 32;
-    // keep at least ~3 CTAs per SM worth of blocks when the batch is small
-    while (G > 8 && (int64_t)rows * ((dim + G - 1) / G) < 3 * 148) G /= 2;
+    const int cand[3] = {128, 96, 64};
+    for (int i = 0; i < 3; ++i) {
+      const int g = cand[i];
+      if (dim % g == 0 && (int64_t)rows * (dim / g) >= 8 * 148) { G = g; break; }
+    }
   } else {
     // one thread per channel: wide groups share the staged B|C|dt_r rows, narrow ones fill the GPU
     G = 32;
@@ -54,5 +58,5 @@ extern "C" int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, in
   }
   if (group_channels) *group_channels = G;
   if (ngroups) *ngroups = (dim + G - 1) / G;
-  return seqlen > 0 ? (seqlen + kT - 1) / kT : 1;
+  return seqlen > 0 ? (seqlen + BIMAMBA_CKPT - 1) / BIMAMBA_CKPT : 1;
 }

@@ -6,91 +6,84 @@
 //   ddelta[t] = sum_n dh a h[t-1] A + u sum_n dh B;  du[t] = g D + delta sum_n dh B
 //   dB[t,n] = sum_d dh delta u;  dC[t,n] = sum_d g h;  dA[n] = sum_t dh a h[t-1] delta
 //
-// Mapping: the backward needs h[t-1] and a[t] of every step while walking time in reverse, so a
-// thread cannot own all 16 states of a channel (16 steps x 16 states x 2 values).  Instead
-//   * lane = state: a half-warp owns one channel, lane n holds state n; a warp works on two
-//     channels at a time and a CTA (4 warps) on a group of <= 32 channels of one (batch, dir).
-//   * time is walked in 16-step chunks from the last to the first.  Per chunk the raw tiles
-//     (u, z, dout, ypre [16 x 32 channels] and the B|C|dt_r rows) are staged by 16-byte cp.async
-//     one chunk ahead; a per-ELEMENT pre-pass computes delta (fused dt projection + softplus),
-//     delta*u, g, dz (stored straight away, coalesced) once and leaves them in shared memory,
-//     from where the recurrence broadcast-reads them four steps per LDS.128.
-//   * the chunk is re-run forward from its checkpoint keeping a[t], h[t] in 32 registers, then
-//     the reverse recurrence runs over the same registers - no (B, L, D, N) tensor, 16 exps
-//     per element.  Sums over n (ddelta, du) are 16-lane shuffle reduce-scatters that land
-//     step j on lane j; du / ddelta go through a shared-memory tile so the global stores are
-//     channel-contiguous.
-//   * dB/dC accumulate in registers over the warp's channels, are combined over the CTA's warps
-//     in fixed order through shared memory and written as per-group partials; dA/dD/dbias are
-//     per-(batch, dir, channel) partials.  All cross-CTA sums are done in fixed order by
-//     bimamba_reduce_partials: the whole backward is deterministic (no atomics).
+// Mapping.  The backward needs h[t-1] and a[t] of every step while walking time in reverse, so a
+// thread cannot keep all 16 states of a channel for a whole chunk.  Instead
+//   * a thread owns a QUAD of states (2 x float2, so the recurrences issue as FMUL2 / FFMA2) of one
+//     channel: lane = 4 * channel_in_warp + quad, a warp works on 8 channels, a CTA (4 warps) on a
+//     "pass" of 32 channels and on `group_channels` = 32 * passes channels of one (batch, dir).
+//   * time is walked in 8-step chunks from the last to the first (8 = the forward's checkpoint
+//     interval).  Per (chunk, pass) the raw tiles (u, dout, z, ypre [8 x 32 channels], the chunk's
+//     B|C|dt_r rows and the 32 x 16 checkpoint tile) are staged by 16-byte cp.async while the
+//     previous item computes; a per-ELEMENT pre-pass computes delta (fused dt projection +
+//     softplus), delta*u, g, dz (stored straight away, channel-contiguous) once and leaves them in
+//     shared memory, from where the recurrence broadcast-reads them four steps per LDS.128.
+//   * the chunk is re-run forward from its checkpoint keeping a[t], h[t] in 64 registers, then the
+//     reverse recurrence runs over the same registers - no (B, L, D, N) tensor, 16 exps per
+//     element.  Sums over n (ddelta, du) are 4 in-thread terms plus a 4-lane reduce-scatter; a
+//     per-element post-pass turns them into du / ddelta with channel-contiguous stores.
+//   * dB/dC accumulate in registers over the passes of a chunk, then are summed over the CTA's 32
+//     (warp, channel) lanes in fixed order through shared memory and written as per-group partials;
+//     dA/dD/dbias are per-(batch, dir, channel) partials.  All cross-CTA sums are done in fixed order
+//     by bimamba_reduce_partials: the whole backward is deterministic (no atomics).
 #include "common.cuh"
 
 namespace bimamba {
 
+constexpr int kBT = BIMAMBA_CKPT;          // steps per backward chunk == checkpoint interval (8)
 constexpr int kBW = 4;                     // warps per CTA
 constexpr int kBThreads = kBW * 32;
-constexpr int kBG = 32;                    // channels per CTA (tile width)
-constexpr int kBKP = kBG / (2 * kBW);      // channel pairs per warp
-constexpr int kDS = 20;                    // floats per channel row of the derived arrays (16 steps + pad)
-constexpr int kOS = kBG + 1;               // row stride of the output tiles [step][channel]
-static_assert(kBG == 2 * kN, "the post-pass maps one thread column to one [dB|dC] column");
+constexpr int kBC = 32;                    // channels per pass
+constexpr int kMaxKP = 4;                  // passes per CTA: group_channels = 32 * passes
+constexpr int kDS = kBT + 4;               // floats per channel row of the derived arrays (8 steps + pad)
+constexpr int kOS = kBC + 1;               // row stride of the [step][channel] tiles
 constexpr int kNDer = 5;                   // derived arrays: delta, delta*u, g, u, d(delta)/d(raw)
+constexpr int kNRaw = 5;                   // raw tiles: u, dout, z, ypre, delta
+constexpr int kRedStride = kBT * 2 * kN + 16;  // floats per (warp, channel) partial in the dB/dC reduction
+constexpr int kEPT = kBT * kBC / kBThreads;    // elements per thread in the pre/post passes (2)
+static_assert(kBC == 2 * kN, "the dB/dC column sum maps one thread column to one [dB|dC] column");
+static_assert(kBT == 8 && kEPT == 2, "tile geometry");
 
-// Sum over the 16 lanes of a half-warp of v[0..15]; lane j (within its half) returns sum of v[j].
+// Sum over the 4 lanes of a quad of v[0..7]; lane q returns the totals of steps 2q and 2q+1.
 // Fixed tree -> deterministic.
-__device__ __forceinline__ float reduce_scatter16(float (&v)[16], int r) {
-  const bool b3 = r & 8, b2 = r & 4, b1 = r & 2, b0 = r & 1;
-  float w8[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = b3 ? v[i] : v[i + 8];
-    const float keep = b3 ? v[i + 8] : v[i];
-    w8[i] = keep + __shfl_xor_sync(kFull, send, 8);
-  }
+__device__ __forceinline__ void reduce_scatter4(const float (&v)[8], int q, float& r0, float& r1) {
+  const bool b1 = q & 2, b0 = q & 1;
   float w4[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float send = b2 ? w8[i] : w8[i + 4];
-    const float keep = b2 ? w8[i + 4] : w8[i];
-    w4[i] = keep + __shfl_xor_sync(kFull, send, 4);
+    const float send = b1 ? v[i] : v[i + 4];
+    const float keep = b1 ? v[i + 4] : v[i];
+    w4[i] = keep + __shfl_xor_sync(kFull, send, 2);
   }
   float w2[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const float send = b1 ? w4[i] : w4[i + 2];
-    const float keep = b1 ? w4[i + 2] : w4[i];
-    w2[i] = keep + __shfl_xor_sync(kFull, send, 2);
+    const float send = b0 ? w4[i] : w4[i + 2];
+    const float keep = b0 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(kFull, send, 1);
   }
-  const float send = b0 ? w2[0] : w2[1];
-  const float keep = b0 ? w2[1] : w2[0];
-  return keep + __shfl_xor_sync(kFull, send, 1);
-}
-
-__device__ __forceinline__ float half_sum(float v) {  // all-reduce over the 16 lanes of a half-warp
-#pragma unroll
-  for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
-  return v;
+  r0 = w2[0];
+  r1 = w2[1];
 }
 
 template <typename T>
 struct BwdSmem {
-  static constexpr int kMaxRaw = 5;  // u, dout, z, ypre, delta
-  static constexpr size_t raw_bytes = (size_t)2 * kMaxRaw * kT * kBG * sizeof(T);
-  static constexpr size_t xr_bytes = (size_t)2 * kT * kXW * sizeof(T);
-  static constexpr size_t f32_floats = kT * kXW + kNDer * kBG * kDS + 2 * kT * kOS + kBW * 2 * kT * kN +
-                                       kBG * BIMAMBA_MAX_DT_RANK + 2 * kBG;
+  static constexpr size_t raw_bytes = (size_t)kNRaw * kBT * kBC * sizeof(T);
+  static constexpr size_t xr_bytes = (size_t)kBT * kXW * sizeof(T);
+  static constexpr size_t f32_floats = kBC * kN /*ckpt tile*/ + kBT * kXW + kNDer * kBC * kDS + 2 * kBT * kOS +
+                                       32 * kRedStride + kMaxKP * kBC * (BIMAMBA_MAX_DT_RANK + 2 + 2 * kN + 2 * kBW);
   static constexpr size_t total = raw_bytes + xr_bytes + f32_floats * sizeof(float);
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kBThreads, 3) scan_bwd_kernel(const bimamba_scan_desc p) {
+__global__ void __launch_bounds__(kBThreads, 2) scan_bwd_kernel(const bimamba_scan_desc p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int b = blockIdx.z, dir = blockIdx.y, G = p.group_channels, g = blockIdx.x, d0 = g * G;
+  const int KP = G / kBC;
   const int ngroups = gridDim.x;
-  const int warp = tid >> 5, lane = tid & 31, half = lane >> 4, n = lane & 15;
-  const int L = p.seqlen, nck = (L + kT - 1) / kT;
+  const int warp = tid >> 5, lane = tid & 31, cw = lane >> 2, q = lane & 3;
+  const int rc = warp * 8 + cw;  // channel of this thread within a pass (recurrence mapping)
+  const int L = p.seqlen, nsub = (L + kBT - 1) / kBT;
   const bool gated = p.z != nullptr, expl = p.delta != nullptr;
   const bool softplus = (p.flags & BIMAMBA_FLAG_SOFTPLUS) != 0;
   const int R = expl ? 0 : p.dt_rank;
@@ -111,20 +104,24 @@ __global__ void __launch_bounds__(kBThreads, 3) scan_bwd_kernel(const bimamba_sc
   // partial layout (batch, ngroups, L, ndir, 32): reducing over ngroups leaves rows ordered (b, t, dir)
   const int64_t pb_ts = (int64_t)p.ndir * 2 * kN;
   float* partB = p.dbc_part + (((int64_t)b * ngroups + g) * L) * pb_ts + dir * 2 * kN;
+  const float* gck = p.ckpt ? p.ckpt + bd * nsub * (int64_t)p.dim * kN : nullptr;
 
   // ---- shared memory carve
   using SM = BwdSmem<T>;
-  T* s_raw = reinterpret_cast<T*>(smem_raw);                       // [2][5][kT*kBG]
-  T* s_xr = reinterpret_cast<T*>(smem_raw + SM::raw_bytes);        // [2][kT*kXW]
-  float* s_xf = reinterpret_cast<float*>(smem_raw + SM::raw_bytes + SM::xr_bytes);  // [kT*kXW]
-  float* s_der = s_xf + kT * kXW;                                  // [5][kBG*kDS]
-  float* s_out = s_der + kNDer * kBG * kDS;                        // [2][kT*kOS]
-  float* s_red = s_out + 2 * kT * kOS;                             // [kBW][kT*32]
-  float* s_wdt = s_red + kBW * 2 * kT * kN;                        // [kBG][16]
-  float* s_bias = s_wdt + kBG * BIMAMBA_MAX_DT_RANK;               // [kBG]
-  float* s_D = s_bias + kBG;                                       // [kBG]
-  float* s_dl = s_der, *s_du = s_der + kBG * kDS, *s_g = s_der + 2 * kBG * kDS, *s_u = s_der + 3 * kBG * kDS,
-        *s_sp = s_der + 4 * kBG * kDS;
+  T* s_raw = reinterpret_cast<T*>(smem_raw);                       // [5][kBT*kBC]
+  T* s_xr = reinterpret_cast<T*>(smem_raw + SM::raw_bytes);        // [kBT*kXW]
+  float* s_ck = reinterpret_cast<float*>(smem_raw + SM::raw_bytes + SM::xr_bytes);  // [kBC*16]
+  float* s_xf = s_ck + kBC * kN;                                   // [kBT*kXW]
+  float* s_der = s_xf + kBT * kXW;                                 // [5][kBC*kDS]
+  float* s_rr = s_der + kNDer * kBC * kDS;                         // [2][kBT*kOS]
+  float* s_red = s_rr + 2 * kBT * kOS;                             // [32][kRedStride]
+  float* s_wdt = s_red + 32 * kRedStride;                          // [G][16]
+  float* s_bias = s_wdt + kMaxKP * kBC * BIMAMBA_MAX_DT_RANK;      // [G]
+  float* s_D = s_bias + kMaxKP * kBC;                              // [G]
+  float* s_m = s_D + kMaxKP * kBC;                                 // [G][16]  reverse carry a*dh
+  float* s_dA = s_m + kMaxKP * kBC * kN;                           // [G][16]
+  float* s_dl = s_der, *s_du = s_der + kBC * kDS, *s_g = s_der + 2 * kBC * kDS, *s_u = s_der + 3 * kBC * kDS,
+        *s_sp = s_der + 4 * kBC * kDS;
 
   constexpr int kV = 16 / sizeof(T);
   const bool dim_vec = (p.dim % kV) == 0 && (d0 % kV) == 0;
@@ -135,258 +132,358 @@ __global__ void __launch_bounds__(kBThreads, 3) scan_bwd_kernel(const bimamba_sc
   const bool vec_dl = expl && dim_vec && aligned16(gdl + d0) && (p.delta_ts % kV) == 0;
   const bool vec_bc = aligned16(gbc) && (p.bc_ts % kV) == 0;
   const bool vec_dtr = R && (p.flags & BIMAMBA_FLAG_DTR_PADDED) && aligned16(gdtr) && (p.dtr_ts % kV) == 0;
+  const bool vec_ck = gck != nullptr && aligned16(gck);  // rows of dim * 16 floats
   const int col_end = min(p.dim, d0 + G);
 
-  auto stage = [&](int c0, int bf) {
+  // Fast staging path (every tensor 16-byte friendly): a fixed (tensor, row, vector) assignment per
+  // thread, so an item costs each thread a handful of address computations and cp.async's.
+  constexpr int VPR = kBC / kV;        // vectors per tile row
+  constexpr int VT = kBT * VPR;        // vectors per activation tile
+  const bool fast = vec_u && vec_do && (!gated || vec_z) && (!need_yp || vec_yp) && (!expl || vec_dl) && vec_bc &&
+                    (!R || vec_dtr) && (!gck || vec_ck);
+  // stage the raw tiles of item (chunk c0, pass k); with_rows also stages the chunk's B|C|dt_r rows
+  auto stage = [&](int c0, int k, bool with_rows) {
     auto row_of = [&](int i) -> int64_t {
-      const int tau = c0 * kT + i;
+      const int tau = c0 * kBT + i;
       return tau < L ? (int64_t)(dir ? (L - 1 - tau) : tau) : (int64_t)-1;
     };
-    T* sa = s_raw + bf * SM::kMaxRaw * kT * kBG;
-    stage_tile(sa, kBG, gu, p.u_ts, kT, kBG, d0, col_end, vec_u, row_of, tid, kBThreads);
-    stage_tile(sa + kT * kBG, kBG, gdo, p.dout_ts, kT, kBG, d0, col_end, vec_do, row_of, tid, kBThreads);
-    if (gated) stage_tile(sa + 2 * kT * kBG, kBG, gz, p.z_ts, kT, kBG, d0, col_end, vec_z, row_of, tid, kBThreads);
-    if (need_yp) stage_tile(sa + 3 * kT * kBG, kBG, gyp, p.out_ts, kT, kBG, d0, col_end, vec_yp, row_of, tid, kBThreads);
-    if (expl) stage_tile(sa + 4 * kT * kBG, kBG, gdl, p.delta_ts, kT, kBG, d0, col_end, vec_dl, row_of, tid, kBThreads);
-    T* sx = s_xr + bf * kT * kXW;
-    stage_tile(sx, kXW, gbc, p.bc_ts, kT, 2 * kN, 0, 2 * kN, vec_bc, row_of, tid, kBThreads);
-    if (R) {
-      const int w = vec_dtr ? 16 : R;
-      stage_tile(sx + 2 * kN, kXW, gdtr, p.dtr_ts, kT, w, 0, w, vec_dtr, row_of, tid, kBThreads);
+    const int c_lo = d0 + k * kBC;
+    if (fast) {
+#pragma unroll
+      for (int it = 0; it < (kNRaw * VT + kBThreads - 1) / kBThreads; ++it) {
+        const int e = tid + it * kBThreads;
+        const int ts_ = e / VT;          // warp-uniform tensor index: 0 u, 1 dout, 2 z, 3 ypre, 4 delta
+        if (ts_ < kNRaw) {
+          const T* gp = ts_ == 0 ? gu : ts_ == 1 ? gdo : ts_ == 2 ? gz : ts_ == 3 ? gyp : gdl;
+          const int64_t gts = ts_ == 0 ? p.u_ts : ts_ == 1 ? p.dout_ts : ts_ == 2 ? p.z_ts : ts_ == 3 ? p.out_ts : p.delta_ts;
+          if (gp != nullptr) {
+            const int r = e - ts_ * VT, i = r / VPR, v = r - i * VPR;
+            const int64_t t = row_of(i);
+            const int c = c_lo + v * kV;
+            const bool ok = t >= 0 && c < col_end;
+            cp_async16(s_raw + ts_ * kBT * kBC + i * kBC + v * kV, ok ? (gp + t * gts + c) : gp, ok);
+          }
+        }
+      }
+      if (gck) {  // 32 channels x 16 states = 128 float4
+        const int c = c_lo + (tid >> 2);
+        const bool ok = c < col_end;
+        cp_async16(s_ck + tid * 4, ok ? (gck + ((int64_t)c0 * p.dim + c) * kN + (tid & 3) * 4) : gck, ok);
+      }
+      if (with_rows) {
+        constexpr int BV = 2 * kN / kV, DV = 16 / kV;   // vectors per row: B|C and padded dt_r
+        const int nv = kBT * (BV + (R ? DV : 0));
+        if (tid < nv) {
+          const int i = tid / (BV + (R ? DV : 0)), v = tid - i * (BV + (R ? DV : 0));
+          const int64_t t = row_of(i);
+          const bool ok = t >= 0;
+          const T* src = v < BV ? (gbc + t * p.bc_ts + v * kV) : (gdtr + t * p.dtr_ts + (v - BV) * kV);
+          cp_async16(s_xr + i * kXW + v * kV, ok ? src : gbc, ok);
+        }
+      }
+      cp_async_commit();
+      return;
+    }
+    stage_tile(s_raw, kBC, gu, p.u_ts, kBT, kBC, c_lo, col_end, vec_u, row_of, tid, kBThreads);
+    stage_tile(s_raw + kBT * kBC, kBC, gdo, p.dout_ts, kBT, kBC, c_lo, col_end, vec_do, row_of, tid, kBThreads);
+    if (gated) stage_tile(s_raw + 2 * kBT * kBC, kBC, gz, p.z_ts, kBT, kBC, c_lo, col_end, vec_z, row_of, tid, kBThreads);
+    if (need_yp) stage_tile(s_raw + 3 * kBT * kBC, kBC, gyp, p.out_ts, kBT, kBC, c_lo, col_end, vec_yp, row_of, tid, kBThreads);
+    if (expl) stage_tile(s_raw + 4 * kBT * kBC, kBC, gdl, p.delta_ts, kBT, kBC, c_lo, col_end, vec_dl, row_of, tid, kBThreads);
+    if (gck) {  // checkpoint tile: channels [c_lo, c_lo+32) x 16 states = one contiguous run of floats
+      auto one = [&](int) -> int64_t { return (int64_t)c0; };
+      stage_tile(s_ck, kBC * kN, gck, (int64_t)p.dim * kN, 1, kBC * kN, c_lo * kN, col_end * kN, vec_ck, one, tid, kBThreads);
+    }
+    if (with_rows) {
+      stage_tile(s_xr, kXW, gbc, p.bc_ts, kBT, 2 * kN, 0, 2 * kN, vec_bc, row_of, tid, kBThreads);
+      if (R) {
+        const int w = vec_dtr ? 16 : R;
+        stage_tile(s_xr + 2 * kN, kXW, gdtr, p.dtr_ts, kBT, w, 0, w, vec_dtr, row_of, tid, kBThreads);
+      }
     }
     cp_async_commit();
   };
 
-  if (nck > 0) stage(nck - 1, (nck - 1) & 1);
+  if (nsub > 0) stage(nsub - 1, 0, true);
 
-  // per-CTA constants
-  for (int e = tid; e < kBG * BIMAMBA_MAX_DT_RANK; e += kBThreads) {
+  // per-CTA constants and accumulators
+  for (int e = tid; e < G * BIMAMBA_MAX_DT_RANK; e += kBThreads) {
     const int cc = e / BIMAMBA_MAX_DT_RANK, r = e % BIMAMBA_MAX_DT_RANK;
     const int c = d0 + cc;
-    s_wdt[e] = (cc < G && c < p.dim && r < R) ? __ldg(p.Wdt + (int64_t)c * R + r) : 0.f;
+    s_wdt[e] = (c < p.dim && r < R) ? __ldg(p.Wdt + (int64_t)c * R + r) : 0.f;
   }
-  for (int cc = tid; cc < kBG; cc += kBThreads) {
+  for (int cc = tid; cc < G; cc += kBThreads) {
     const int c = d0 + cc;
-    const bool okc = cc < G && c < p.dim;
-    s_bias[cc] = (okc && p.delta_bias) ? __ldg(p.delta_bias + c) : 0.f;
-    s_D[cc] = (okc && p.D) ? __ldg(p.D + c) : 0.f;
+    s_bias[cc] = (c < p.dim && p.delta_bias) ? __ldg(p.delta_bias + c) : 0.f;
+    s_D[cc] = (c < p.dim && p.D) ? __ldg(p.D + c) : 0.f;
+  }
+  for (int e = tid; e < G * kN; e += kBThreads) {
+    s_m[e] = 0.f;
+    s_dA[e] = 0.f;
+  }
+  if (!gck) {
+    for (int e = tid; e < kBC * kN; e += kBThreads) s_ck[e] = 0.f;  // single chunk: the start state is zero
   }
 
-  float A2[kBKP], Dd[kBKP], dDacc[kBKP], dbacc[kBKP], mcar[kBKP], dAacc[kBKP];
-  int ch[kBKP];
+  float* s_acc = s_dA + kMaxKP * kBC * kN;  // [2][kBW][kMaxKP*kBC]: dD / dbias partial of (warp, channel)
+  for (int e = tid; e < 2 * kBW * kMaxKP * kBC; e += kBThreads) s_acc[e] = 0.f;
+  float2 dBa[kBT][2], dCa[kBT][2];
 #pragma unroll
-  for (int k = 0; k < kBKP; ++k) {
-    const int cl = 2 * (warp + kBW * k) + half;
-    const int c = d0 + cl;
-    const bool ok = cl < G && c < p.dim;
-    ch[k] = ok ? c : -1;
-    A2[k] = ok ? __ldg(p.A + (int64_t)c * kN + n) * kLog2e : 0.f;
-    Dd[k] = (ok && p.D) ? __ldg(p.D + c) : 0.f;
-    dDacc[k] = 0.f;
-    dbacc[k] = 0.f;
-    mcar[k] = 0.f;
-    dAacc[k] = 0.f;
+  for (int i = 0; i < kBT; ++i) {
+    dBa[i][0] = dBa[i][1] = make_float2(0.f, 0.f);
+    dCa[i][0] = dCa[i][1] = make_float2(0.f, 0.f);
   }
   const int R4 = (R + 3) >> 2;
+  const int pcc = tid & (kBC - 1);  // channel (within a pass) of this thread in the pre / post passes
 
-  for (int c0 = nck - 1; c0 >= 0; --c0) {
-    const int bf = c0 & 1;
-    const int tau0 = c0 * kT;
-    cp_async_wait<0>();
-    __syncthreads();  // (1) chunk c0 tiles visible; previous chunk's post-pass done
-    if (c0 > 0) stage(c0 - 1, bf ^ 1);
-
-    // ---- pre-pass: one element (step i, channel cc) per thread-iteration
-    {
-      const T* sx = s_xr + bf * kT * kXW;
-      const int valid = 2 * kN + R;
-      for (int e = tid; e < kT * kXW; e += kBThreads) {
-        const int col = e % kXW;
-        s_xf[e] = col < valid ? to_f(sx[e]) : 0.f;
+  for (int c0 = nsub - 1; c0 >= 0; --c0) {
+    const int tau0 = c0 * kBT;
+#pragma unroll 1
+    for (int k = 0; k < KP; ++k) {
+      cp_async_wait<0>();
+      __syncthreads();  // (1) this item's tiles are visible; the previous item's post-pass is done
+      if (k == 0) {
+        const int valid = 2 * kN + R;
+        for (int e = tid; e < kBT * kXW; e += kBThreads) {
+          const int col = e % kXW;
+          s_xf[e] = col < valid ? to_f(s_xr[e]) : 0.f;
+        }
+        __syncthreads();  // dt_r rows are read by the pre-pass below
       }
-    }
-    __syncthreads();  // s_xf ready (dt_r rows are read below)
-    {
-      const T* sa = s_raw + bf * SM::kMaxRaw * kT * kBG;
-      const int cc = tid & (kBG - 1);
-      const int c = d0 + cc;
-      const bool okc = cc < G && c < p.dim;
-      const float bias = s_bias[cc];
+      // start state of this thread's (channel, quad) for the chunk, read before the tile is recycled
+      const float4 hs = *reinterpret_cast<const float4*>(s_ck + rc * kN + 4 * q);
+
+      // ---- pre-pass: one element (step i, channel pcc) per thread-iteration
+      {
+        const int cg = k * kBC + pcc;  // channel within the group
+        const int c = d0 + cg;
+        const bool okc = c < p.dim && cg < G;
+        const float bias = s_bias[cg];
 #pragma unroll
-      for (int j = 0; j < kT * kBG / kBThreads; ++j) {
-        const int i = (tid >> 5) + j * (kBThreads / kBG);
-        const int tau = tau0 + i;
-        float dl = 0.f, dlu = 0.f, gg = 0.f, uu = 0.f, sp = 0.f;
-        if (okc && tau < L) {
-          const int e = i * kBG + cc;
-          uu = to_f(sa[e]);
-          const float dov = to_f(sa[kT * kBG + e]);
-          float draw = bias;
-          if (expl) {
-            draw += to_f(sa[4 * kT * kBG + e]);
-          } else {
-            const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW + 2 * kN);
-            const float4* wr = reinterpret_cast<const float4*>(s_wdt + cc * BIMAMBA_MAX_DT_RANK);
+        for (int j = 0; j < kEPT; ++j) {
+          const int i = (tid >> 5) + j * (kBThreads / kBC);
+          const int tau = tau0 + i;
+          float dl = 0.f, dlu = 0.f, gg = 0.f, uu = 0.f, sp = 0.f;
+          if (okc && tau < L) {
+            const int e = i * kBC + pcc;
+            uu = to_f(s_raw[e]);
+            const float dov = to_f(s_raw[kBT * kBC + e]);
+            float draw = bias;
+            if (expl) {
+              draw += to_f(s_raw[4 * kBT * kBC + e]);
+            } else {
+              const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW + 2 * kN);
+              const float4* wr = reinterpret_cast<const float4*>(s_wdt + cg * BIMAMBA_MAX_DT_RANK);
+              float2 acc0 = make_float2(draw, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q < R4) {
-                const float4 x = xr[q], w = wr[q];
-                draw = fmaf(w.x, x.x, draw);
-                draw = fmaf(w.y, x.y, draw);
-                draw = fmaf(w.z, x.z, draw);
-                draw = fmaf(w.w, x.w, draw);
+              for (int r4 = 0; r4 < 4; ++r4) {
+                if (r4 < R4) {
+                  const float4 x = xr[r4], w = wr[r4];
+                  acc0 = __ffma2_rn(make_float2(w.x, w.y), make_float2(x.x, x.y), acc0);
+                  acc1 = __ffma2_rn(make_float2(w.z, w.w), make_float2(x.z, x.w), acc1);
+                }
+              }
+              draw = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+            }
+            if (softplus) {
+              dl = softplus_f(draw);
+              sp = draw > 20.f ? 1.f : sigmoid_f(draw);
+            } else {
+              dl = draw;
+              sp = 1.f;
+            }
+            dlu = dl * uu;
+            gg = dov;
+            if (gated) {
+              const float zz = to_f(s_raw[2 * kBT * kBC + e]);
+              const float sg = sigmoid_f(zz);
+              gg = dov * zz * sg;
+              if (need_yp) {
+                const float yp = to_f(s_raw[3 * kBT * kBC + e]);
+                const int64_t t = dir ? (L - 1 - tau) : tau;
+                gdz[t * p.out_ts + c] = from_f<T>(dov * yp * sg * (1.f + zz * (1.f - sg)));
               }
             }
           }
-          if (softplus) {
-            dl = softplus_f(draw);
-            sp = draw > 20.f ? 1.f : sigmoid_f(draw);
-          } else {
-            dl = draw;
-            sp = 1.f;
-          }
-          dlu = dl * uu;
-          gg = dov;
-          if (gated) {
-            const float zz = to_f(sa[2 * kT * kBG + e]);
-            const float sg = sigmoid_f(zz);
-            gg = dov * zz * sg;
-            if (need_yp) {
-              const float yp = to_f(sa[3 * kT * kBG + e]);
-              const int64_t t = dir ? (L - 1 - tau) : tau;
-              gdz[t * p.out_ts + c] = from_f<T>(dov * yp * sg * (1.f + zz * (1.f - sg)));
+          const int o = pcc * kDS + i;
+          s_dl[o] = dl;
+          s_du[o] = dlu;
+          s_g[o] = gg;
+          s_u[o] = uu;
+          s_sp[o] = sp;
+        }
+      }
+      __syncthreads();  // (2) derived arrays ready; raw tiles, checkpoint tile and (k == 0) raw rows are free
+      {                 // prefetch the next item
+        int nk = k + 1, nc = c0;
+        if (nk >= KP) {
+          nk = 0;
+          nc = c0 - 1;
+        }
+        if (nc >= 0) stage(nc, nk, nk == 0);
+      }
+
+      // ---- recurrence: this thread owns states 4q..4q+3 of channel rc of the pass
+      {
+        const int cg = k * kBC + rc;
+        const int c = d0 + cg;
+        float4 A4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < p.dim && cg < G) A4 = __ldg(reinterpret_cast<const float4*>(p.A + (int64_t)c * kN) + q);
+        const float2 A2a = make_float2(A4.x * kLog2e, A4.y * kLog2e), A2b = make_float2(A4.z * kLog2e, A4.w * kLog2e);
+        const float4* pd = reinterpret_cast<const float4*>(s_dl + rc * kDS);
+        const float4* pu = reinterpret_cast<const float4*>(s_du + rc * kDS);
+        const float4* pg = reinterpret_cast<const float4*>(s_g + rc * kDS);
+
+        // re-run the chunk forward from the checkpoint, keeping a[t], h[t]
+        float2 a[kBT][2], hh[kBT][2];
+        {
+          float2 h0 = make_float2(hs.x, hs.y), h1 = make_float2(hs.z, hs.w);
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const float4 d4 = pd[hq], u4 = pu[hq];
+            const float dq[4] = {d4.x, d4.y, d4.z, d4.w}, uq[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * hq + e;
+              const float4 B4 = *reinterpret_cast<const float4*>(s_xf + i * kXW + 4 * q);
+              const float2 dd = make_float2(dq[e], dq[e]), uu = make_float2(uq[e], uq[e]);
+              const float2 x0 = __fmul2_rn(dd, A2a), x1 = __fmul2_rn(dd, A2b);
+              a[i][0] = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+              a[i][1] = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+              h0 = __ffma2_rn(a[i][0], h0, __fmul2_rn(uu, make_float2(B4.x, B4.y)));
+              h1 = __ffma2_rn(a[i][1], h1, __fmul2_rn(uu, make_float2(B4.z, B4.w)));
+              hh[i][0] = h0;
+              hh[i][1] = h1;
             }
           }
         }
-        const int o = cc * kDS + i;
-        s_dl[o] = dl;
-        s_du[o] = dlu;
-        s_g[o] = gg;
-        s_u[o] = uu;
-        s_sp[o] = sp;
-      }
-    }
-    __syncthreads();  // (2) derived arrays ready
-
-    // ---- recurrence
-    float Bv[kT], Cv[kT], dBa[kT], dCa[kT];
+        // reverse recurrence:  dh_i = g_i C_i + m_{i+1},  m_i = a_i dh_i
+        float4* pm = reinterpret_cast<float4*>(s_m + cg * kN + 4 * q);
+        const float4 m4 = *pm;
+        float2 m0 = make_float2(m4.x, m4.y), m1 = make_float2(m4.z, m4.w);
+        float2 dA0 = make_float2(0.f, 0.f), dA1 = make_float2(0.f, 0.f);
+        float vA[kBT], vU[kBT];
 #pragma unroll
-    for (int i = 0; i < kT; ++i) {
-      Bv[i] = s_xf[i * kXW + n];
-      Cv[i] = s_xf[i * kXW + kN + n];
-      dBa[i] = 0.f;
-      dCa[i] = 0.f;
-    }
+        for (int hq = 1; hq >= 0; --hq) {
+          const float4 d4 = pd[hq], u4 = pu[hq], g4 = pg[hq];
+          const float dq[4] = {d4.x, d4.y, d4.z, d4.w}, uq[4] = {u4.x, u4.y, u4.z, u4.w},
+                      gq[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-    for (int k = 0; k < kBKP; ++k) {
-      // warp-uniform skip: the pair index is out of range for the whole warp
-      if (2 * (warp + kBW * k) >= G || d0 + 2 * (warp + kBW * k) >= p.dim) continue;
-      const int c = ch[k];
-      const bool ok = c >= 0;
-      const int cl = 2 * (warp + kBW * k) + half;
-      const float hstart = (ok && c0 > 0) ? p.ckpt[(((bd * nck + c0) * p.dim) + c) * kN + n] : 0.f;
-      const float4* pd = reinterpret_cast<const float4*>(s_dl + cl * kDS);
-      const float4* pu = reinterpret_cast<const float4*>(s_du + cl * kDS);
-      const float4* pg = reinterpret_cast<const float4*>(s_g + cl * kDS);
-
-      // re-run the chunk forward, keeping a[t], h[t]
-      float a[kT], hh[kT];
-      const float a2 = A2[k];
-      {
-        float hk = hstart;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 d4 = pd[q], u4 = pu[q];
-          const float dq[4] = {d4.x, d4.y, d4.z, d4.w}, uq[4] = {u4.x, u4.y, u4.z, u4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = 4 * q + e;
-            a[i] = ex2_approx(dq[e] * a2);
-            hk = fmaf(a[i], hk, uq[e] * Bv[i]);
-            hh[i] = hk;
+          for (int e = 3; e >= 0; --e) {
+            const int i = 4 * hq + e;
+            const float4 B4 = *reinterpret_cast<const float4*>(s_xf + i * kXW + 4 * q);
+            const float4 C4 = *reinterpret_cast<const float4*>(s_xf + i * kXW + kN + 4 * q);
+            const float2 gg = make_float2(gq[e], gq[e]), dd = make_float2(dq[e], dq[e]), uu = make_float2(uq[e], uq[e]);
+            const float2 dh0 = __ffma2_rn(gg, make_float2(C4.x, C4.y), m0);
+            const float2 dh1 = __ffma2_rn(gg, make_float2(C4.z, C4.w), m1);
+            m0 = __fmul2_rn(a[i][0], dh0);
+            m1 = __fmul2_rn(a[i][1], dh1);
+            const float2 hp0 = (i == 0) ? make_float2(hs.x, hs.y) : hh[i == 0 ? 0 : i - 1][0];
+            const float2 hp1 = (i == 0) ? make_float2(hs.z, hs.w) : hh[i == 0 ? 0 : i - 1][1];
+            const float2 da0 = __fmul2_rn(m0, hp0), da1 = __fmul2_rn(m1, hp1);
+            dA0 = __ffma2_rn(da0, dd, dA0);
+            dA1 = __ffma2_rn(da1, dd, dA1);
+            dBa[i][0] = __ffma2_rn(dh0, uu, dBa[i][0]);
+            dBa[i][1] = __ffma2_rn(dh1, uu, dBa[i][1]);
+            dCa[i][0] = __ffma2_rn(gg, hh[i][0], dCa[i][0]);
+            dCa[i][1] = __ffma2_rn(gg, hh[i][1], dCa[i][1]);
+            const float2 ta = __ffma2_rn(da1, A2b, __fmul2_rn(da0, A2a));
+            const float2 tu = __ffma2_rn(dh1, make_float2(B4.z, B4.w), __fmul2_rn(dh0, make_float2(B4.x, B4.y)));
+            vA[i] = ta.x + ta.y;   // sum_n dh a h[t-1] A (x log2e; scaled back in the post-pass)
+            vU[i] = tu.x + tu.y;   // sum_n dh B
           }
         }
+        *pm = make_float4(m0.x, m0.y, m1.x, m1.y);
+        float4* pa = reinterpret_cast<float4*>(s_dA + cg * kN + 4 * q);
+        float4 acc = *pa;
+        acc.x += dA0.x;
+        acc.y += dA0.y;
+        acc.z += dA1.x;
+        acc.w += dA1.y;
+        *pa = acc;
+        float rA0, rA1, rU0, rU1;
+        reduce_scatter4(vA, q, rA0, rA1);
+        reduce_scatter4(vU, q, rU0, rU1);
+        s_rr[(2 * q) * kOS + rc] = rA0;
+        s_rr[(2 * q + 1) * kOS + rc] = rA1;
+        s_rr[kBT * kOS + (2 * q) * kOS + rc] = rU0;
+        s_rr[kBT * kOS + (2 * q + 1) * kOS + rc] = rU1;
       }
-      // reverse recurrence:  dh_i = g_i C_i + m_{i+1},  m_i = a_i dh_i
-      float m = mcar[k];
-      float dAl = 0.f;
-#pragma unroll
-      for (int q = 3; q >= 0; --q) {
-        const float4 d4 = pd[q], u4 = pu[q], g4 = pg[q];
-        const float dq[4] = {d4.x, d4.y, d4.z, d4.w}, uq[4] = {u4.x, u4.y, u4.z, u4.w},
-                    gq[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-        for (int e = 3; e >= 0; --e) {
-          const int i = 4 * q + e;
-          const float dh = fmaf(gq[e], Cv[i], m);
-          m = a[i] * dh;
-          const float hp = (i == 0) ? hstart : hh[i - 1];
-          const float daa = m * hp;
-          dAl = fmaf(daa, dq[e], dAl);
-          dBa[i] = fmaf(dh, uq[e], dBa[i]);
-          dCa[i] = fmaf(gq[e], hh[i], dCa[i]);
-          a[i] = daa * a2;      // a[i] is dead: reuse as the d(delta) partial (x ln2 later)
-          hh[i] = dh * Bv[i];   // hh[i] is dead for the remaining steps: the d(delta*u) partial
-        }
-      }
-      mcar[k] = m;
-      dAacc[k] += dAl;
-      const float rA = reduce_scatter16(a, n);
-      const float rU = reduce_scatter16(hh, n);
-      // epilogue: lane n owns step n of this channel
+      __syncthreads();  // (3) per-(step, channel) sums ready
+
+      // ---- post-pass: du, ddelta (channel-contiguous stores), dD / dbias accumulation
       {
-        const int o = cl * kDS + n;
-        const float uj = s_u[o], dj = s_dl[o], gj = s_g[o], sp = s_sp[o];
-        dDacc[k] = fmaf(gj, uj, dDacc[k]);
-        const float duv = fmaf(gj, Dd[k], dj * rU);
-        const float ddl = fmaf(uj, rU, rA * kLn2) * sp;
-        dbacc[k] += ddl;
-        s_out[n * kOS + cl] = duv;
-        s_out[kT * kOS + n * kOS + cl] = ddl;
+        const int cg = k * kBC + pcc;
+        const int c = d0 + cg;
+        const bool okc = c < p.dim && cg < G;
+        const float Dd = s_D[cg];
+        float dDl = 0.f, dbl = 0.f;
+#pragma unroll
+        for (int j = 0; j < kEPT; ++j) {
+          const int i = (tid >> 5) + j * (kBThreads / kBC);
+          const int tau = tau0 + i;
+          if (okc && tau < L) {
+            const int o = pcc * kDS + i;
+            const float uj = s_u[o], dj = s_dl[o], gj = s_g[o], sp = s_sp[o];
+            const float rA = s_rr[i * kOS + pcc], rU = s_rr[kBT * kOS + i * kOS + pcc];
+            dDl = fmaf(gj, uj, dDl);
+            const float duv = fmaf(gj, Dd, dj * rU);
+            const float ddl = fmaf(uj, rU, rA * kLn2) * sp;
+            dbl += ddl;
+            const int64_t t = dir ? (L - 1 - tau) : tau;
+            gdu[t * p.out_ts + c] = from_f<T>(duv);
+            gdd[t * p.out_ts + c] = from_f<T>(ddl);
+          }
+        }
+        s_acc[warp * (kMaxKP * kBC) + cg] += dDl;   // this thread is the only writer of these two slots
+        s_acc[(kBW + warp) * (kMaxKP * kBC) + cg] += dbl;
       }
-    }
-    // ---- dB/dC of this chunk: halves by shuffle, warps through shared memory (fixed order)
+    }  // passes
+
+    // ---- dB/dC of this chunk: sum over the CTA's 32 (warp, channel) lanes in fixed order
     {
-      float* myRed = s_red + warp * (2 * kT * kN);
+      float* my = s_red + (warp * 8 + cw) * kRedStride;
 #pragma unroll
-      for (int i = 0; i < kT; ++i) {
-        const float vb = dBa[i] + __shfl_xor_sync(kFull, dBa[i], 16);
-        const float vc = dCa[i] + __shfl_xor_sync(kFull, dCa[i], 16);
-        myRed[i * 2 * kN + lane] = half ? vc : vb;  // row i: [dB_0..15 | dC_0..15]
+      for (int i = 0; i < kBT; ++i) {
+        *reinterpret_cast<float4*>(my + i * 2 * kN + 4 * q) = make_float4(dBa[i][0].x, dBa[i][0].y, dBa[i][1].x, dBa[i][1].y);
+        *reinterpret_cast<float4*>(my + i * 2 * kN + kN + 4 * q) = make_float4(dCa[i][0].x, dCa[i][0].y, dCa[i][1].x, dCa[i][1].y);
+        dBa[i][0] = dBa[i][1] = make_float2(0.f, 0.f);
+        dCa[i][0] = dCa[i][1] = make_float2(0.f, 0.f);
       }
     }
-    __syncthreads();  // (3) output tiles and per-warp dB/dC tiles complete
+    __syncthreads();  // (4)
 #pragma unroll
-    for (int j = 0; j < kT * kBG / kBThreads; ++j) {
-      const int i = (tid >> 5) + j * (kBThreads / kBG);
-      const int cc = tid & (kBG - 1);
+    for (int j = 0; j < kEPT; ++j) {
+      const int i = (tid >> 5) + j * (kBThreads / kBC);
       const int tau = tau0 + i;
       if (tau < L) {
-        const int64_t t = dir ? (L - 1 - tau) : tau;
-        if (cc < G && d0 + cc < p.dim) {
-          gdu[t * p.out_ts + d0 + cc] = from_f<T>(s_out[i * kOS + cc]);
-          gdd[t * p.out_ts + d0 + cc] = from_f<T>(s_out[kT * kOS + i * kOS + cc]);
-        }
         float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kBW; ++w) s += s_red[w * (2 * kT * kN) + i * 2 * kN + cc];
-        partB[t * pb_ts + cc] = s;
+#pragma unroll 8
+        for (int w = 0; w < 32; ++w) s += s_red[w * kRedStride + i * 2 * kN + pcc];
+        const int64_t t = dir ? (L - 1 - tau) : tau;
+        partB[t * pb_ts + pcc] = s;
       }
     }
-    // the next iteration's barrier (1) orders these reads before the tiles are rewritten
+    // the next item's barrier (1) orders these reads before s_red is rewritten
   }
 
+  // ---- per-channel partials
+  __syncthreads();
+  for (int e = tid; e < G * kN; e += kBThreads) {
+    const int c = d0 + e / kN;
+    if (c < p.dim) p.dA_part[(bd * p.dim + c) * kN + (e % kN)] = s_dA[e];
+  }
+  // dD / dbias: 4 threads (one per warp) share a channel; combine in fixed order
+  for (int cg = tid; cg < G; cg += kBThreads) {
+    const int c = d0 + cg;
+    if (c < p.dim) {
+      float sD = 0.f, sb = 0.f;
 #pragma unroll
-  for (int k = 0; k < kBKP; ++k) {
-    const float sD = half_sum(dDacc[k]);
-    const float sb = half_sum(dbacc[k]);
-    const int c = ch[k];
-    if (c >= 0) {
-      p.dA_part[(bd * p.dim + c) * kN + n] = dAacc[k];
-      if (n == 0) {
-        if (p.dD_part) p.dD_part[bd * p.dim + c] = sD;
-        if (p.dbias_part) p.dbias_part[bd * p.dim + c] = sb;
+      for (int w = 0; w < kBW; ++w) {
+        sD += s_acc[w * (kMaxKP * kBC) + cg];
+        sb += s_acc[(kBW + w) * (kMaxKP * kBC) + cg];
       }
+      if (p.dD_part) p.dD_part[bd * p.dim + c] = sD;
+      if (p.dbias_part) p.dbias_part[bd * p.dim + c] = sb;
     }
   }
 }
@@ -410,7 +507,7 @@ extern "C" int bimamba_selective_scan_bwd(const bimamba_scan_desc* d, bimamba_st
   int rc = check_desc(d, true);
   if (rc) return rc;
   const int G = d->group_channels;
-  if (G < 2 || G > kBG || (G & 1)) { set_err("backward group_channels must be even, 2..32 (use bimamba_scan_plan)"); return -5; }
+  if (G < kBC || G > kMaxKP * kBC || (G % kBC)) { set_err("backward group_channels must be 32, 64, 96 or 128 (use bimamba_scan_plan)"); return -5; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (d->io_dtype) {
     case BIMAMBA_F32: launch_bwd<float>(d, st); break;

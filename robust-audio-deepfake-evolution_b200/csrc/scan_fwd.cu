@@ -20,7 +20,7 @@
 //   * direction 1 walks the same storage back to front (t = L-1-step): flip(M(flip(x))) of
 //     src/models/DualStreamSEMamba.py:476-478 with no flipped copy; both directions are
 //     blockIdx.y of the same launch.
-//   * training forward also writes the fp32 state entering every chunk ("checkpoints",
+//   * training forward also writes the fp32 state entering every 8-step chunk ("checkpoints",
 //     (B, dir, chunk, D, 16): 64 contiguous bytes per thread) and the pre-gate y; the backward
 //     recomputes the states of a chunk from its checkpoint (no (B, L, D, N) tensor).
 #include "common.cuh"
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
   const int G = blockDim.x, tid = threadIdx.x;
   const int b = blockIdx.z, dir = blockIdx.y, d0 = blockIdx.x * G, d = d0 + tid;
   const bool ok = d < p.dim;
-  const int L = p.seqlen, nck = (L + kT - 1) / kT;
+  const int L = p.seqlen, nck = (L + kT - 1) / kT, nckpt = (L + BIMAMBA_CKPT - 1) / BIMAMBA_CKPT;
   const bool softplus = (p.flags & BIMAMBA_FLAG_SOFTPLUS) != 0;
   const int R = expl ? 0 : p.dt_rank;
 
@@ -129,16 +129,16 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
     }
     __syncthreads();
     if (ok) {
-      if (p.ckpt) {
-        float4* ck = reinterpret_cast<float4*>(
-            p.ckpt + ((((int64_t)b * p.ndir + dir) * nck + c0) * p.dim + d) * kN);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ck[q] = make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y);
-      }
       const T* su = s_act + bf * nact * kT * G + tid;
       const int nvalid = L - c0 * kT;  // steps of this chunk that exist (>= 1)
 #pragma unroll 2
       for (int i = 0; i < kT; ++i) {
+        if ((i & (BIMAMBA_CKPT - 1)) == 0 && p.ckpt && i < nvalid) {  // state entering this 8-step chunk
+          float4* ck = reinterpret_cast<float4*>(
+              p.ckpt + ((((int64_t)b * p.ndir + dir) * nckpt + (c0 * kT + i) / BIMAMBA_CKPT) * p.dim + d) * kN);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ck[q] = make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y);
+        }
         const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW);
         const float u = to_f(su[i * G]);
         float draw;
