@@ -1,0 +1,94 @@
+"""CPU-side checks of the drop-in boundary (no compute calls: there is no GPU here):
+the C-ABI library loads, exports every function include/bimamba.h declares, the ctypes mirror of
+`struct bimamba_scan_desc` has the C layout, argument errors come back as codes (nothing throws),
+and the Python surface mirrors the reference's names and refuses CPU tensors (no fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+import bimamba_b200 as bm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "bimamba.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bimamba_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = bm._lib.load()
+    names = _declared_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/bimamba.h but not exported"
+    assert sorted(bm._lib.EXPORTS) == names, "the ctypes binding must type exactly the declared entry points"
+    assert lib.bimamba_abi_version() == bm._lib.ABI_VERSION
+
+
+def test_scan_desc_layout_matches_header(tmp_path):
+    """sizeof / offsetof of the ctypes mirror against the C compiler's view of the header."""
+    prog = tmp_path / "layout.c"
+    fields = [f[0] for f in bm._lib.ScanDesc._fields_]
+    body = "\n".join(f'  printf("{f} %zu\\n", offsetof(bimamba_scan_desc, {f}));' for f in fields)
+    prog.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{HEADER}"\nint main(void) {{\n'
+                    f'  printf("sizeof %zu\\n", sizeof(bimamba_scan_desc));\n{body}\n  return 0;\n}}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", str(prog), "-o", str(exe)])
+    out = dict(ln.split() for ln in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(out["sizeof"]) == C.sizeof(bm._lib.ScanDesc)
+    for f in fields:
+        assert int(out[f]) == getattr(bm._lib.ScanDesc, f).offset, f
+
+
+def test_argument_errors_are_codes_not_exceptions():
+    lib = bm._lib.load()
+    assert lib.bimamba_selective_scan_fwd(None, None) == -1
+    assert b"null descriptor" in lib.bimamba_last_error()
+    d = bm._lib.ScanDesc()
+    d.batch, d.ndir, d.dim, d.seqlen, d.dstate = 1, 1, 8, 4, 8          # d_state 8 is not supported
+    assert lib.bimamba_selective_scan_fwd(C.byref(d), None) == -2
+    d.dstate = 16
+    assert lib.bimamba_selective_scan_bwd(C.byref(d), None) < 0          # null operands
+    assert lib.bimamba_causal_conv1d_fwd(None, None, None, None, 1, 1, 8, 4, 4, 0, 0, 0, 0, 0, 0, 0, None) == -1
+    assert lib.bimamba_layernorm_fwd(None, None, None, None, None, None, 4, 8, 1e-5, 0, 0, None) == -1
+    # empty problems are a no-op success (the reference accepts zero-length batches)
+    d.batch = 0
+    assert lib.bimamba_selective_scan_fwd(C.byref(d), None) == 0
+    assert lib.bimamba_reduce_partials(None, None, 0, 0, 0, 0, 0, 0, 0, 0, None) == 0
+
+
+def test_scan_plan_geometry():
+    for L, dim, rows, bwd in [(201, 288, 128, False), (201, 288, 128, True), (8192, 288, 64, True), (1, 17, 1, False)]:
+        g, ng, nck = bm._lib.scan_plan(L, dim, rows, bwd)
+        assert g % 32 == 0 and 32 <= g <= 128
+        assert ng == -(-dim // g)
+        assert nck == -(-L // 8)
+
+
+def test_python_surface_mirrors_reference_and_has_no_cpu_fallback():
+    m = bm.Mamba(144, 16)                                   # DualStreamSEMamba.py:455 positional call
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert shapes == {
+        "A_log": (288, 16), "D": (288,), "in_proj.weight": (576, 144), "conv1d.weight": (288, 1, 4),
+        "conv1d.bias": (288,), "x_proj.weight": (41, 288), "dt_proj.weight": (288, 9), "dt_proj.bias": (288,),
+        "out_proj.weight": (144, 288)}
+    enc = bm.PN_BiMambas_Encoder(144, 16)                   # DualStreamSEMamba.py:451-465 attribute names
+    assert {n for n, _ in enc.named_children()} == {"mamba", "norm1", "norm2", "feed_forward"}
+    x = torch.randn(2, 5, 144)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bm.selective_scan_fn(torch.zeros(1, 8, 4), torch.zeros(1, 8, 4), -torch.ones(8, 16), torch.zeros(1, 16, 4),
+                             torch.zeros(1, 16, 4))
+    pkg = bm.install_mamba_ssm_shim()
+    from mamba_ssm.modules.mamba_simple import Mamba as ShimMamba   # the import at DualStreamSEMamba.py:43
+    assert ShimMamba is bm.Mamba and pkg.Mamba is bm.Mamba
