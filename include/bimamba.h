@@ -136,9 +136,9 @@ int bimamba_causal_conv1d_fwd(const void* x, const float* weight, const float* b
  * (batch, ndir, L, dim) gate gradients with dout's strides; when given their sum over
  * directions is written to dz_out (batch, L, dim) with dx's strides, so the in_proj backward
  * reads one [dx | dz] matrix.  dwb_part: (nslices, dim, K+1) fp32 partials
- * [dw_0..dw_{K-1}, dbias] with nslices = bimamba_conv_bwd_slices(batch, seqlen); reduce over
+ * [dw_0..dw_{K-1}, dbias] with nslices = bimamba_conv_bwd_slices(batch, seqlen, dim); reduce over
  * slices with bimamba_reduce_partials. */
-int bimamba_conv_bwd_slices(int batch, int seqlen);
+int bimamba_conv_bwd_slices(int batch, int seqlen, int dim);
 int bimamba_causal_conv1d_bwd(const void* x, const float* weight, const float* bias, const void* dout,
                               void* dx, const void* dz_in, void* dz_out, float* dwb_part,
                               int batch, int ndir, int dim, int seqlen, int width,

@@ -85,7 +85,7 @@ def load() -> C.CDLL:
         lib.bimamba_causal_conv1d_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                                   i64, i64, i64, i64, i64, i64, i64, i32, i32, vp]
         lib.bimamba_conv_bwd_slices.restype = i32
-        lib.bimamba_conv_bwd_slices.argtypes = [i32, i32]
+        lib.bimamba_conv_bwd_slices.argtypes = [i32, i32, i32]
         lib.bimamba_reduce_partials.restype = i32
         lib.bimamba_reduce_partials.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp]
         f32 = C.c_float

@@ -18,7 +18,6 @@ namespace bimamba {
 constexpr int kSeg = 16;          // time steps per thread
 constexpr int kConvThreads = 128;
 constexpr int kMaxK = 4;
-constexpr int kConvSY = 8;        // time slots per batch row in the backward (partials per batch = kConvSY)
 
 template <typename T, int V> struct Vec;
 template <> struct Vec<float, 4> { using type = float4; };
@@ -87,8 +86,10 @@ conv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const floa
       for (int i = 0; i < V; ++i) win[j + 1][i] = 0.f;
     }
   }
-  const int tend = min(L, t0 + kSeg);
-  for (int t = t0; t < tend; ++t) {
+#pragma unroll
+  for (int s_ = 0; s_ < kSeg; ++s_) {
+    const int t = t0 + s_;
+    if (t >= L) break;
 #pragma unroll
     for (int j = 0; j < 2 * H; ++j)
 #pragma unroll
@@ -123,7 +124,7 @@ conv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const floa
 }
 
 // Backward.  Thread = (batch b, time slot y, channel vector v); it walks the segments
-// s = y, y+kConvSY, ... of its row.  For a segment [t0, t0+kSeg):
+// s = y, y+SY, ... of its row (SY = time slots per batch row, conv_sy()).  For a segment [t0, t0+kSeg):
 //   pre_dir[t] = bias + sum_k w[k] x[t -/+ (H-k)];  g_dir[t] = dout_dir[t] * silu'(pre_dir[t])
 //   dx[tau]    = sum_k w[k] ( g_0[tau+H-k] + g_1[tau-H+k] )
 //   dw[k]     += sum_t g_0[t] x[t-H+k] + g_1[t] x[t+H-k];   dbias += sum_t g_0[t] + g_1[t]
@@ -182,8 +183,9 @@ conv_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const floa
         for (int i = 0; i < V; ++i) xw[j + 1][i] = 0.f;
       }
     }
-    const int tau_end = t0 + kSeg + H;
-    for (int tau = t0 - H; tau < tau_end; ++tau) {
+#pragma unroll
+    for (int s_ = 0; s_ < kSeg + 2 * H; ++s_) {
+      const int tau = t0 - H + s_;
 #pragma unroll
       for (int j = 0; j < 2 * H; ++j)
 #pragma unroll
@@ -294,9 +296,13 @@ reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t gr
   }
 }
 
-static int conv_sy(int seqlen) {
+// time slots per batch row in the backward: enough threads to fill the GPU, few enough partials
+static int conv_sy(int batch, int seqlen, int dim) {
   const int nseg = (seqlen + kSeg - 1) / kSeg;
-  return nseg < kConvSY ? (nseg < 1 ? 1 : nseg) : kConvSY;
+  const int64_t per_slot = (int64_t)(batch < 1 ? 1 : batch) * ((dim + 3) / 4);
+  int64_t sy = (150000 + per_slot - 1) / per_slot;
+  if (sy > nseg) sy = nseg;
+  return (int)(sy < 1 ? 1 : sy);
 }
 
 template <typename T, int V>
@@ -320,7 +326,7 @@ static void launch_conv_bwd(const void* x, const float* w, const float* bias, co
                             const void* dz_in, void* dz_out, float* part, int batch, int ndir, int dim, int L, int width,
                             int64_t x_bs, int64_t x_ts, int64_t g_bs, int64_t g_ds, int64_t g_ts, int64_t dx_bs,
                             int64_t dx_ts, int silu, cudaStream_t st) {
-  const int nvec = (dim + V - 1) / V, SY = conv_sy(L);
+  const int nvec = (dim + V - 1) / V, SY = conv_sy(batch, L, dim);
   const int64_t total = (int64_t)batch * SY * nvec;
   const unsigned blocks = (unsigned)((total + kConvThreads - 1) / kConvThreads);
   const T* xp = reinterpret_cast<const T*>(x);
@@ -370,7 +376,7 @@ extern "C" int bimamba_causal_conv1d_fwd(const void* x, const float* weight, con
   return 0;
 }
 
-extern "C" int bimamba_conv_bwd_slices(int batch, int seqlen) { return batch * conv_sy(seqlen); }
+extern "C" int bimamba_conv_bwd_slices(int batch, int seqlen, int dim) { return batch * conv_sy(batch, seqlen, dim); }
 
 extern "C" int bimamba_causal_conv1d_bwd(const void* x, const float* weight, const float* bias, const void* dout, void* dx,
                                          const void* dz_in, void* dz_out, float* dwb_part, int batch, int ndir, int dim,

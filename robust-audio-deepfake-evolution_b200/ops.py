@@ -127,7 +127,7 @@ def conv_bwd_raw(x, weight, bias, dout, dx, silu: bool, dz_in=None, dz_out=None)
             raise ValueError("dz_in must share dout's strides")
         if (dz_out.stride(0), dz_out.stride(1)) != (dx.stride(0), dx.stride(1)):
             raise ValueError("dz_out must share dx's strides")
-    nsl = lib.bimamba_conv_bwd_slices(Bsz, L)
+    nsl = lib.bimamba_conv_bwd_slices(Bsz, L, D)
     part = torch.empty((max(nsl, 1), D, K + 1), device=x.device, dtype=torch.float32)
     with _timed("conv_bwd"):
         rc = lib.bimamba_causal_conv1d_bwd(
@@ -518,7 +518,8 @@ class BiMambaInnerFn(torch.autograd.Function):
             Wd_pad = torch.zeros((D, XW - 2 * N), device=dd2.device, dtype=cd)
             Wd_pad[:, :R] = Wd32
             dxdbl = torch.cat([rows2d(dbc), torch.mm(dd2, Wd_pad)], dim=1)    # (M*ndir, 48) [dB | dC | ddt_r | 0]
-            dW_dt = torch.mm(dd2.t(), xdbl[:, 2 * N:2 * N + R])               # (D, R)
+            dW_dt = torch.mm(dd2.t(), xdbl)[:, 2 * N:2 * N + R]               # (D, R); full-row GEMM: a 9-column strided
+                                                                              # operand would fall off cuBLAS's fast kernels
             # x_proj
             xc2 = rows2d(xc)
             dW_xp = torch.mm(dxdbl.t(), xc2)                                  # (48, D)
