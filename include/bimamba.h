@@ -22,6 +22,9 @@
  *                                       and its autograd
  *   bimamba_reduce_partials          <- the sum over batch/time/direction that
  *                                       autograd performs for parameter gradients
+ *   bimamba_layernorm_fwd/bwd        <- nn.LayerNorm of the encoder layer (DualStreamSEMamba.py:472,482)
+ *   bimamba_gemm_nt                  <- the nn.Linear calls of mamba_block.py:48,73,62
+ *                                       (in_proj, x_proj, out_proj) on tcgen05 tensor cores
  *
  * Ownership: the library never allocates or frees device memory.  All tensors and
  * workspaces are caller-allocated; pointers are borrowed for the duration of the
@@ -166,6 +169,18 @@ int bimamba_layernorm_bwd_blocks(int64_t rows);
 int bimamba_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean,
                           const float* rstd, void* dx, float* dgb_part, int64_t rows, int channels,
                           int x_dtype, int dy_dtype, bimamba_stream_t stream);
+
+/* C[M, N] = A[M, K] . B[N, K]^T (+ bias[N]) (+ addend[M, N]) with bf16 / fp16 operands (row-major, K contiguous, row strides
+ * lda / ldb in elements, multiples of 8, 16-byte aligned bases) and fp32 accumulation on the tcgen05 tensor
+ * cores (TMA-fed, TMEM accumulator).  C has out_dtype (fp32 or the operand dtype) and row stride ldc.  This is
+ * nn.Linear: in_proj / x_proj / out_proj (mamba_block.py:48, :73, :62), the feed-forward Linears
+ * (DualStreamSEMamba.py:460-464) and, with B = W^T, their data gradients.  Ragged M, N, K are handled by the
+ * TMA unit's zero fill.  addend (optional) has C's dtype and row stride (residual / accumulate-into).
+ * bimamba_gemm_nt_block_n(N) is the tile width the kernel will use. */
+int bimamba_gemm_nt_block_n(int N);
+int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                    const float* bias, const void* addend, int64_t M, int N, int K, int in_dtype, int out_dtype,
+                    bimamba_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,305 @@
+// C[M, N] = A[M, K] . B[N, K]^T (+ bias) on the 5th-generation tensor cores.  sm_100a only.
+//
+// Reference: the nn.Linear projections of the Bi-Mamba block - in_proj (mamba_block.py:22,48),
+// x_proj (:33,73), out_proj (:39,62) - and the data-gradient GEMMs of their autograd, plus the two
+// Linear layers of the encoder's feed-forward (DualStreamSEMamba.py:460-464).  All of them are
+// "NT" products of row-major (K-major) bf16/fp16 operands with fp32 accumulation.
+//
+// Structure (one 128 x BLOCK_N output tile per CTA, 4 warps):
+//   * warp 0, one elected lane: TMA producer.  `cp.async.bulk.tensor.2d` (UTMALDG) loads 128 x 64
+//     and BLOCK_N x 64 boxes of A and B into a ring of shared-memory stages in the 128-byte
+//     swizzled K-major layout the tensor core reads; rows / columns beyond M, N, K are zero-filled by
+//     the TMA unit, so ragged shapes (K = 144, N = 48, M = B*L) need no padding copies.
+//   * warp 1, one elected lane: MMA issuer.  `tcgen05.mma.cta_group::1.kind::f16` (UTCHMMA),
+//     M = 128, N = BLOCK_N, K = 16 per instruction, accumulating in TMEM; `tcgen05.commit` releases
+//     each stage back to the producer and finally signals the epilogue.
+//   * all 4 warps: epilogue.  `tcgen05.ld` (LDTM) moves the accumulator rows (one TMEM lane per
+//     thread) to registers 16 columns at a time; bias add, conversion and 16/32-byte global stores.
+// Stages, full/empty mbarriers and the TMEM allocation follow the usual sm_100 pipeline.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace bimamba {
+
+constexpr int kGM = 128;       // tile rows (UMMA M)
+constexpr int kGK = 64;        // K per stage: 64 x 2 B = one 128-byte swizzle row
+constexpr int kGStagesMax = 4;
+constexpr int kGThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// K-major, 128-byte swizzle: 8-row atoms of 1024 bytes; LBO = 1 (unused), SBO = 1024 B, version 1.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(kGThreads)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               TOut* __restrict__ C, const float* __restrict__ bias, const TOut* __restrict__ addend, int M, int N,
+               int K, int64_t ldc, int block_n,
+               int stages, uint32_t idesc, uint32_t tmem_cols) {
+  extern __shared__ __align__(1024) unsigned char gsm[];
+  __shared__ __align__(8) uint64_t full_bar[kGStagesMax], empty_bar[kGStagesMax], accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kGM, n0 = blockIdx.y * block_n;
+  const int nkb = (K + kGK - 1) / kGK;
+  const uint32_t a_bytes = kGM * kGK * 2, b_bytes = (uint32_t)block_n * kGK * 2;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);  // keep every operand 1024-byte aligned
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gsm) + 1023) & ~(uintptr_t)1023);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % stages;
+      if (kb >= stages) mbar_wait(&empty_bar[s], ((kb / stages) - 1) & 1);
+      unsigned char* sa = base + (size_t)s * stage_bytes;
+      mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+      tma_load_2d(sa, &map_a, &full_bar[s], kb * kGK, m0);
+      tma_load_2d(sa + a_bytes, &map_b, &full_bar[s], kb * kGK, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % stages;
+      mbar_wait(&full_bar[s], (kb / stages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+      const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sa + a_bytes);
+#pragma unroll
+      for (int k = 0; k < kGK / 16; ++k) {
+        // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
+        umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[s]);  // frees this stage when the MMAs above have read it
+    }
+    umma_commit(&accum_bar);       // accumulator complete
+  }
+  __syncwarp();  // lanes 1..31 of the two role warps park here instead of spinning next to their leader
+
+  // ---- epilogue: all warps; thread = one accumulator row (TMEM lane)
+  mbar_wait(&accum_bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncwarp();
+  const int row = warp * 32 + lane;
+  const int m = m0 + row;
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int c = 0; c < block_n; c += 16) {
+    uint32_t r[16];
+    tmem_ld16(trow + (uint32_t)c, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int n = n0 + c;
+    if (m < M && n < N) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = __uint_as_float(r[j]);
+        if (bias != nullptr && n + j < N) v[j] += __ldg(bias + n + j);
+      }
+      TOut* dst = C + (int64_t)m * ldc + n;
+      if (addend != nullptr) {
+        const TOut* src = addend + (int64_t)m * ldc + n;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < N) v[j] += to_f(src[j]);
+      }
+      if (n + 16 <= N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        if (sizeof(TOut) == 2) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const TOut lo = from_f<TOut>(v[2 * j]), hi = from_f<TOut>(v[2 * j + 1]);
+            pk[j] = (uint32_t)(*reinterpret_cast<const unsigned short*>(&lo)) |
+                    ((uint32_t)(*reinterpret_cast<const unsigned short*>(&hi)) << 16);
+          }
+          reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < N) dst[j] = from_f<TOut>(v[j]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_err("cuTensorMapEncodeTiled is not available from the driver"); return -20; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kGK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == BIMAMBA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_err("cuTensorMapEncodeTiled failed (operand must be 16-byte aligned with a row stride that is a multiple of 8 elements)"); return -21; }
+  return 0;
+}
+
+}  // namespace bimamba
+
+using namespace bimamba;
+
+extern "C" int bimamba_gemm_nt_block_n(int N) {
+  // largest tile width (multiple of 16, <= 256) that divides N into equal tiles with little waste
+  if (N <= 0) return 0;
+  const int n16 = (N + 15) / 16 * 16;
+  if (n16 <= 256) return n16;
+  int best = 256, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 64; bn -= 16) {
+    const int tiles = (N + bn - 1) / bn;
+    const int waste = tiles * bn - N;
+    if (waste < best_waste) { best = bn; best_waste = waste; }
+  }
+  return best;
+}
+
+extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                               const float* bias, const void* addend, int64_t M, int N, int K, int in_dtype,
+                               int out_dtype, bimamba_stream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  if (!A || !B || !C) { set_err("gemm: null operand"); return -1; }
+  if (M < 0 || N < 0 || K < 1) { set_err("gemm: bad sizes"); return -3; }
+  if (in_dtype != BIMAMBA_BF16 && in_dtype != BIMAMBA_F16) { set_err("gemm: operands must be bf16 or fp16 (fp32 products stay on the fp32 library path)"); return -6; }
+  if (out_dtype < 0 || out_dtype > 2 || (out_dtype != BIMAMBA_F32 && out_dtype != in_dtype)) { set_err("gemm: output must be fp32 or the operand dtype"); return -6; }
+  if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) {
+    set_err("gemm: operands must be 16-byte aligned with row strides that are multiples of 8 elements");
+    return -7;
+  }
+  if (M > (int64_t)kGM * 2147483647LL / 2) { set_err("gemm: M too large"); return -3; }
+  const int block_n = bimamba_gemm_nt_block_n(N);
+  CUtensorMap map_a, map_b;
+  int rc = make_map(&map_a, A, in_dtype, M, K, lda, kGM);
+  if (rc) return rc;
+  rc = make_map(&map_b, B, in_dtype, N, K, ldb, block_n);
+  if (rc) return rc;
+  const int nkb = (K + kGK - 1) / kGK;
+  const uint32_t stage_bytes = kGM * kGK * 2 + (((uint32_t)block_n * kGK * 2 + 1023u) & ~1023u);
+  int stages = (int)((96u * 1024u) / stage_bytes);
+  if (stages > kGStagesMax) stages = kGStagesMax;
+  if (stages > nkb) stages = nkb;
+  if (stages < 1) stages = 1;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < block_n) tmem_cols <<= 1;
+  // instruction descriptor: D fp32, A/B bf16|fp16, both K-major, N >> 3, M >> 4
+  const uint32_t fmt = in_dtype == BIMAMBA_BF16 ? 1u : 0u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kGM >> 4) << 24);
+  dim3 grid((unsigned)((M + kGM - 1) / kGM), (unsigned)((N + block_n - 1) / block_n));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define GEMM_LAUNCH(TOUT)                                                                                          \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(gemm_nt_kernel<TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    gemm_nt_kernel<TOUT><<<grid, kGThreads, smem, st>>>(map_a, map_b, reinterpret_cast<TOUT*>(C), bias,             \
+                                                         reinterpret_cast<const TOUT*>(addend), (int)M, N, K, ldc, \
+                                                         block_n, stages, idesc, tmem_cols);                       \
+  } while (0)
+  if (out_dtype == BIMAMBA_F32) GEMM_LAUNCH(float);
+  else if (out_dtype == BIMAMBA_BF16) GEMM_LAUNCH(__nv_bfloat16);
+  else GEMM_LAUNCH(__half);
+#undef GEMM_LAUNCH
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}

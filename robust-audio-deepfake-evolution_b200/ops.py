@@ -21,6 +21,7 @@ keep the upstream (batch, channel, time) signature and transpose at the boundary
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -349,6 +350,42 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     if return_last_state:
         raise NotImplementedError("return_last_state is not used by the reference path")
     return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus)
+
+
+# ----------------------------------------------------------------------------------------
+# projections: C = A . B^T on the tcgen05 tensor cores (mamba_block.py:48, :73, :62)
+# ----------------------------------------------------------------------------------------
+TC_GEMM = os.environ.get("BIMAMBA_GEMM", "tcgen05") != "cublas"   # cublas = library GEMMs (A/B comparison only)
+
+
+def _tc_ok(A: torch.Tensor, B: torch.Tensor) -> bool:
+    return (TC_GEMM and A.dtype in (torch.bfloat16, torch.float16) and B.dtype == A.dtype and A.dim() == 2
+            and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1 and A.stride(0) % 8 == 0
+            and B.stride(0) % 8 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and A.shape[0] > 0)
+
+
+def gemm_nt(A, B, bias=None, addend=None, out_dtype=None):
+    """A (M, K) . B (N, K)^T (+ bias (N) fp32) (+ addend (M, N)) -> (M, N).  bf16 / fp16 operands run on this
+    repository's tcgen05 kernel; fp32 operands (the 1e-4 parity mode) stay on the fp32 library GEMM."""
+    out_dtype = out_dtype or A.dtype
+    if not _tc_ok(A, B):
+        C_ = torch.mm(A, B.t()).to(out_dtype)
+        if bias is not None:
+            C_ = C_ + bias.to(out_dtype)
+        if addend is not None:
+            C_ = C_ + addend
+        return C_
+    lib = _lib.load()
+    M, K = A.shape
+    N = B.shape[0]
+    out = torch.empty((M, N), device=A.device, dtype=out_dtype)
+    if addend is not None:
+        if addend.dtype != out_dtype or addend.shape != out.shape or not addend.is_contiguous():
+            addend = addend.to(out_dtype).contiguous()
+    with _timed("gemm_nt"):
+        _lib.check(lib.bimamba_gemm_nt(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), N, _ptr(bias),
+                                       _ptr(addend), M, N, K, _dt(A), _dt(out), _stream()), "bimamba_gemm_nt")
+    return out
 
 
 # ----------------------------------------------------------------------------------------

@@ -180,3 +180,35 @@ def test_layer_norm(C, dtype, out_dtype):
     assert rel(xd.grad, xr.grad) < tol
     assert rel(wd.grad, wr.grad) < tol
     assert rel(bd.grad, br.grad) < tol
+
+
+# ---------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 48, 288), (12864, 576, 144), (25728, 48, 288), (12864, 144, 576),
+                                   (201, 288, 48), (1, 16, 8), (300, 41 + 7, 144), (257, 640, 72)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gemm_nt_tensor_cores(M, N, K, dtype):
+    """nn.Linear products of the block (mamba_block.py:48, :73, :62) on the tcgen05 kernel against an fp64 product
+    of the same rounded operands; bias, addend, fp32 output, ragged M / N / K."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dtype)
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).to(dtype)
+    bias = torch.randn(N, generator=g)
+    add = torch.randn(M, N, generator=g).to(dtype)
+    ref = A.double() @ B.double().t()
+    Ad, Bd = A.cuda(), B.cuda()
+    out = bm.ops.gemm_nt(Ad, Bd)
+    assert out.dtype == dtype and out.shape == (M, N)
+    assert rel(out, ref) < (4e-3 if dtype == torch.bfloat16 else 1e-3)
+    out32 = bm.ops.gemm_nt(Ad, Bd, bias=bias.cuda(), out_dtype=torch.float32)
+    assert rel(out32, ref + bias.double()) < 1e-5          # fp32 accumulation, exact operands
+    out_add = bm.ops.gemm_nt(Ad, Bd, addend=add.cuda())
+    assert rel(out_add, ref + add.double()) < (4e-3 if dtype == torch.bfloat16 else 1e-3)
+
+
+def test_gemm_nt_strided_operand():
+    """A as a column slice of a wider matrix (the x half of xz): lda > K."""
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(500, 576, generator=g).to(torch.bfloat16).cuda()
+    W = (torch.randn(48, 288, generator=g) / 17).to(torch.bfloat16).cuda()
+    out = bm.ops.gemm_nt(big[:, :288], W, out_dtype=torch.float32)
+    assert rel(out, big[:, :288].double() @ W.double().t()) < 1e-5
