@@ -176,8 +176,9 @@ int bimamba_layernorm_bwd(const void* x, const void* dy, const float* gamma, con
  * nn.Linear: in_proj / x_proj / out_proj (mamba_block.py:48, :73, :62), the feed-forward Linears
  * (DualStreamSEMamba.py:460-464) and, with B = W^T, their data gradients.  Ragged M, N, K are handled by the
  * TMA unit's zero fill.  addend (optional) has C's dtype and row stride (residual / accumulate-into).
- * bimamba_gemm_nt_block_n(N) is the tile width the kernel will use. */
+ * bimamba_gemm_nt_block_n_k(N, K) is the tile width the kernel will use. */
 int bimamba_gemm_nt_block_n(int N);
+int bimamba_gemm_nt_block_n_k(int N, int K);
 int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                     const float* bias, const void* addend, int64_t M, int N, int K, int in_dtype, int out_dtype,
                     bimamba_stream_t stream);

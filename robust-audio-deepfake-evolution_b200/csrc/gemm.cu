@@ -18,6 +18,9 @@
 // Stages, full/empty mbarriers and the TMEM allocation follow the usual sm_100 pipeline.
 #include <cuda.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bimamba {
@@ -75,6 +78,47 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// 16 fp32 accumulators (+ bias) -> 16 outputs in a padded shared-memory row
+template <typename TOut>
+__device__ __forceinline__ void stage16(TOut* dst, const uint32_t* r, const float* bias, int n, int N) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = __uint_as_float(r[j]);
+    if (bias != nullptr && n + j < N) v[j] += __ldg(bias + n + j);
+  }
+  if constexpr (sizeof(TOut) == 2) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      } else {
+        const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+    }
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+}
+
 // K-major, 128-byte swizzle: 8-row atoms of 1024 bytes; LBO = 1 (unused), SBO = 1024 B, version 1.
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -91,7 +135,7 @@ __global__ void __launch_bounds__(kGThreads)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                TOut* __restrict__ C, const float* __restrict__ bias, const TOut* __restrict__ addend, int M, int N,
                int K, int64_t ldc, int block_n,
-               int stages, uint32_t idesc, uint32_t tmem_cols) {
+               int stages, uint32_t idesc, uint32_t tmem_cols, int staged) {
   extern __shared__ __align__(1024) unsigned char gsm[];
   __shared__ __align__(8) uint64_t full_bar[kGStagesMax], empty_bar[kGStagesMax], accum_bar;
   __shared__ uint32_t tmem_slot;
@@ -101,7 +145,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int nkb = (K + kGK - 1) / kGK;
   const uint32_t a_bytes = kGM * kGK * 2, b_bytes = (uint32_t)block_n * kGK * 2;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);  // keep every operand 1024-byte aligned
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gsm) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte aligned start of the stages; derived by offset (not by integer casts) so that the compiler keeps
+  // the shared address space and the epilogue's tile accesses are STS / LDS, not generic stores
+  unsigned char* base = gsm + ((1024u - (smem_u32(gsm) & 1023u)) & 1023u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -156,47 +202,74 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncwarp();
   const int row = warp * 32 + lane;
-  const int m = m0 + row;
   const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-  for (int c = 0; c < block_n; c += 16) {
-    uint32_t r[16];
-    tmem_ld16(trow + (uint32_t)c, r);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const int n = n0 + c;
-    if (m < M && n < N) {
-      float v[16];
+  if (staged) {
+    // TMEM -> registers -> padded shared tile (the pipeline stages are free: every MMA has completed),
+    // then row-contiguous 16-byte global stores (and addend loads) by consecutive threads.
+    const int row_bytes = block_n * (int)sizeof(TOut) + 16;  // +16: consecutive rows start 4 banks apart
+    unsigned char* tile = base;
+    unsigned char* my_row = tile + (size_t)row * row_bytes;
+    int c = 0;
+    for (; c + 32 <= block_n; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(trow + (uint32_t)c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      stage16<TOut>(reinterpret_cast<TOut*>(my_row) + c, r, bias, n0 + c, N);
+      stage16<TOut>(reinterpret_cast<TOut*>(my_row) + c + 16, r + 16, bias, n0 + c + 16, N);
+    }
+    if (c < block_n) {
+      uint32_t r[16];
+      tmem_ld16(trow + (uint32_t)c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      stage16<TOut>(reinterpret_cast<TOut*>(my_row) + c, r, bias, n0 + c, N);
+    }
+    __syncthreads();
+    constexpr int EV = 16 / sizeof(TOut);          // elements per 16-byte vector
+    const int vpr = block_n / EV;                  // vectors per tile row (block_n is a multiple of 16)
+    const int drr = kGThreads / vpr, dvv = kGThreads % vpr;
+    int rr = (int)threadIdx.x / vpr, vv = (int)threadIdx.x % vpr;
+    const int total = kGM * vpr;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < total; idx += kGThreads) {
+      const int m = m0 + rr, n = n0 + vv * EV;
+      if (m < M && n < N) {   // N is a multiple of EV on this path
+        uint4 val = *reinterpret_cast<const uint4*>(tile + (size_t)rr * row_bytes + (size_t)vv * 16);
+        TOut* dst = C + (int64_t)m * ldc + n;
+        if (addend != nullptr) {
+          const uint4 ad = *reinterpret_cast<const uint4*>(addend + (int64_t)m * ldc + n);
+          TOut* pv = reinterpret_cast<TOut*>(&val);
+          const TOut* pa = reinterpret_cast<const TOut*>(&ad);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] = __uint_as_float(r[j]);
-        if (bias != nullptr && n + j < N) v[j] += __ldg(bias + n + j);
-      }
-      TOut* dst = C + (int64_t)m * ldc + n;
-      if (addend != nullptr) {
-        const TOut* src = addend + (int64_t)m * ldc + n;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n + j < N) v[j] += to_f(src[j]);
-      }
-      if (n + 16 <= N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        if (sizeof(TOut) == 2) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const TOut lo = from_f<TOut>(v[2 * j]), hi = from_f<TOut>(v[2 * j + 1]);
-            pk[j] = (uint32_t)(*reinterpret_cast<const unsigned short*>(&lo)) |
-                    ((uint32_t)(*reinterpret_cast<const unsigned short*>(&hi)) << 16);
-          }
-          reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < EV; ++j) pv[j] = from_f<TOut>(to_f(pv[j]) + to_f(pa[j]));
         }
-      } else {
+        *reinterpret_cast<uint4*>(dst) = val;
+      }
+      rr += drr;
+      vv += dvv;
+      if (vv >= vpr) {
+        vv -= vpr;
+        ++rr;
+      }
+    }
+  } else {
+    const int m = m0 + row;
+    for (int c = 0; c < block_n; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(trow + (uint32_t)c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int n = n0 + c;
+      if (m < M && n < N) {
+        TOut* dst = C + (int64_t)m * ldc + n;
+        const TOut* src = addend != nullptr ? addend + (int64_t)m * ldc + n : nullptr;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n + j < N) dst[j] = from_f<TOut>(v[j]);
+        for (int j = 0; j < 16; ++j) {
+          if (n + j < N) {
+            float v = __uint_as_float(r[j]);
+            if (bias != nullptr) v += __ldg(bias + n + j);
+            if (src != nullptr) v += to_f(src[j]);
+            dst[j] = from_f<TOut>(v);
+          }
+        }
       }
     }
   }
@@ -241,19 +314,29 @@ static int make_map(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, 
 
 using namespace bimamba;
 
-extern "C" int bimamba_gemm_nt_block_n(int N) {
-  // largest tile width (multiple of 16, <= 256) that divides N into equal tiles with little waste
+// These projections are short-K, bandwidth/latency-bound products: what pays is many co-resident CTAs per SM
+// whose load / MMA / epilogue phases overlap each other, i.e. a small shared-memory and TMEM footprint:
+// two stages and tiles of at most 128 accumulator columns when N allows it (measured, tools/bench_gemm.py).
+static int gemm_stages(int block_n, int K) {
+  const int nkb = (K + kGK - 1) / kGK;
+  (void)block_n;
+  return nkb < 2 ? 1 : 2;
+}
+
+extern "C" int bimamba_gemm_nt_block_n_k(int N, int K) {
+  (void)K;
   if (N <= 0) return 0;
-  const int n16 = (N + 15) / 16 * 16;
-  if (n16 <= 256) return n16;
-  int best = 256, best_waste = 1 << 30;
-  for (int bn = 256; bn >= 64; bn -= 16) {
+  int best = 0;
+  long best_cost = 1L << 60;
+  for (int bn = 256; bn >= 16; bn -= 16) {
     const int tiles = (N + bn - 1) / bn;
-    const int waste = tiles * bn - N;
-    if (waste < best_waste) { best = bn; best_waste = waste; }
+    const long waste = (long)tiles * bn - N;
+    const long cost = waste * 8 + tiles * 32 + (bn > 128 ? 200 : 0);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
+extern "C" int bimamba_gemm_nt_block_n(int N) { return bimamba_gemm_nt_block_n_k(N, 0); }
 
 extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                const float* bias, const void* addend, int64_t M, int N, int K, int in_dtype,
@@ -268,19 +351,25 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
     return -7;
   }
   if (M > (int64_t)kGM * 2147483647LL / 2) { set_err("gemm: M too large"); return -3; }
-  const int block_n = bimamba_gemm_nt_block_n(N);
+  int block_n = bimamba_gemm_nt_block_n_k(N, K);
+  int max_stages = kGStagesMax;
+  if (const char* ov = getenv("BIMAMBA_GEMM_BN")) block_n = atoi(ov);        // tuning experiments only
+  if (const char* ov = getenv("BIMAMBA_GEMM_STAGES")) max_stages = atoi(ov);  // tuning experiments only
   CUtensorMap map_a, map_b;
   int rc = make_map(&map_a, A, in_dtype, M, K, lda, kGM);
   if (rc) return rc;
   rc = make_map(&map_b, B, in_dtype, N, K, ldb, block_n);
   if (rc) return rc;
-  const int nkb = (K + kGK - 1) / kGK;
   const uint32_t stage_bytes = kGM * kGK * 2 + (((uint32_t)block_n * kGK * 2 + 1023u) & ~1023u);
-  int stages = (int)((96u * 1024u) / stage_bytes);
-  if (stages > kGStagesMax) stages = kGStagesMax;
-  if (stages > nkb) stages = nkb;
-  if (stages < 1) stages = 1;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  int stages = gemm_stages(block_n, K);
+  if (stages > max_stages) stages = max_stages;
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+  // staged epilogue: 16-byte aligned output rows and a tile that fits next to (in place of) the stages
+  const int osize = out_dtype == BIMAMBA_F32 ? 4 : 2;
+  const size_t tile_bytes = (size_t)kGM * ((size_t)block_n * osize + 16);
+  int staged = (N % (16 / osize) == 0) && (ldc % (16 / osize) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+               (!addend || (reinterpret_cast<uintptr_t>(addend) & 15) == 0) && tile_bytes <= 110 * 1024;
+  if (staged && tile_bytes + 1024 > smem) smem = tile_bytes + 1024;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < block_n) tmem_cols <<= 1;
   // instruction descriptor: D fp32, A/B bf16|fp16, both K-major, N >> 3, M >> 4
@@ -293,7 +382,7 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
     cudaFuncSetAttribute(gemm_nt_kernel<TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     gemm_nt_kernel<TOUT><<<grid, kGThreads, smem, st>>>(map_a, map_b, reinterpret_cast<TOUT*>(C), bias,             \
                                                          reinterpret_cast<const TOUT*>(addend), (int)M, N, K, ldc, \
-                                                         block_n, stages, idesc, tmem_cols);                       \
+                                                         block_n, stages, idesc, tmem_cols, staged);               \
   } while (0)
   if (out_dtype == BIMAMBA_F32) GEMM_LAUNCH(float);
   else if (out_dtype == BIMAMBA_BF16) GEMM_LAUNCH(__nv_bfloat16);

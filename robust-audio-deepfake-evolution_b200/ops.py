@@ -475,8 +475,9 @@ class BiMambaInnerFn(torch.autograd.Function):
     Uses: in_proj(flip x) = flip(in_proj x) so xz is computed once; the reverse
     direction reads the same x, z back to front; out_proj is ONE GEMM over [y_fwd | y_rev] against
     [W_out | W_out].  The dt projection (K = 9) is fused into the scan kernels.
-    GEMMs are library calls in this version (cuBLAS through torch.matmul); conv, scan, dt_proj and
-    all reductions are this repository's CUDA kernels.
+    In bf16 / fp16 the forward and data-gradient GEMMs run on this repository's tcgen05 kernel (gemm_nt);
+    weight-gradient GEMMs (contraction over B*L) and the fp32 parity mode use the library GEMM.  Conv, scan,
+    dt_proj and all reductions are this repository's CUDA kernels.
     """
 
     @staticmethod
@@ -505,18 +506,18 @@ class BiMambaInnerFn(torch.autograd.Function):
             D32, bdt32 = _f32c(Dp), _f32c(b_dt)
 
             x2 = x.detach().to(cdtype).reshape(M, dm)
-            xz = torch.mm(x2, Wi.t())                                         # (M, 2D)   mamba_block.py:48
+            xz = gemm_nt(x2, Wi)                                              # (M, 2D)   mamba_block.py:48
             xz3 = xz.view(Bsz, L, 2 * D)
             xs, z = xz3[:, :, :D], xz3[:, :, D:]                              # :49 (views)
             xc = per_dir(Bsz, L, ndir, D, dev, cdtype)
             conv_fwd_raw(xs, cw32, cb32, xc, True)                            # :52-55, both directions
-            xdbl = torch.mm(rows2d(xc), Wxp.t())                              # (M*ndir, 48)   :73
+            xdbl = gemm_nt(rows2d(xc), Wxp)                                   # (M*ndir, 48)   :73
             xd4 = xdbl.view(Bsz, L, ndir, XW).permute(0, 2, 1, 3)
             needs_bwd = any(ctx.needs_input_grad)
             y, ckpt, ypre = scan_fwd_raw(xc, z.unsqueeze(1).expand(Bsz, ndir, L, D), None, xd4[..., :2 * N],
                                          xd4[..., 2 * N:], Wd32, A32, D32, bdt32, True, needs_bwd,
                                          dtr_padded=True)                     # :80-120, :61
-            out = torch.mm(rows2d(y).view(M, ndir * D), Wo2.t()).view(Bsz, L, dm)   # :62 + DualStreamSEMamba.py:481
+            out = gemm_nt(rows2d(y).view(M, ndir * D), Wo2).view(Bsz, L, dm)  # :62 + DualStreamSEMamba.py:481
             if needs_bwd:
                 ctx.save_for_backward(x2, xz, xc, xdbl, y, Wi, Wxp, Wd32, Wo, cw32, cb32, A32, D32, bdt32,
                                       ckpt if ckpt is not None else torch.empty(0), ypre)
@@ -541,7 +542,7 @@ class BiMambaInnerFn(torch.autograd.Function):
 
             g2 = dout.to(cd).reshape(M, dm)
             # out_proj
-            dy = torch.mm(g2, Wo)                                             # (M, D), shared by both directions
+            dy = gemm_nt(g2, Wo.t().contiguous())                             # (M, D), shared by both directions
             y2 = rows2d(y).view(M, ndir * D)
             dW_out2 = torch.mm(g2.t(), y2)                                    # (dm, ndir*D)
             dW_out = dW_out2[:, :D] + dW_out2[:, D:] if ndir > 1 else dW_out2
@@ -552,15 +553,15 @@ class BiMambaInnerFn(torch.autograd.Function):
                 A32, D32, bdt32, True, dyb, ckpt, ypre, dtr_padded=True)
             # dt_proj (weight gradient in fp32; the data gradient joins the x_proj row)
             dd2 = rows2d(ddelta)                                              # (M*ndir, D)
-            Wd_pad = torch.zeros((D, XW - 2 * N), device=dd2.device, dtype=cd)
-            Wd_pad[:, :R] = Wd32
-            dxdbl = torch.cat([rows2d(dbc), torch.mm(dd2, Wd_pad)], dim=1)    # (M*ndir, 48) [dB | dC | ddt_r | 0]
+            WdT_pad = torch.zeros((XW - 2 * N, D), device=dd2.device, dtype=cd)
+            WdT_pad[:R] = Wd32.t()
+            dxdbl = torch.cat([rows2d(dbc), gemm_nt(dd2, WdT_pad)], dim=1)    # (M*ndir, 48) [dB | dC | ddt_r | 0]
             dW_dt = torch.mm(dd2.t(), xdbl)[:, 2 * N:2 * N + R]               # (D, R); full-row GEMM: a 9-column strided
                                                                               # operand would fall off cuBLAS's fast kernels
             # x_proj
             xc2 = rows2d(xc)
             dW_xp = torch.mm(dxdbl.t(), xc2)                                  # (48, D)
-            dxc = torch.addmm(rows2d(du), dxdbl, Wxp)                         # (M*ndir, D)
+            dxc = gemm_nt(dxdbl, Wxp.t().contiguous(), addend=rows2d(du))     # (M*ndir, D)
             dxc4 = dxc.view(Bsz, L, ndir, D).permute(0, 2, 1, 3)
             # conv (writes dx into the x half and dz_fwd + dz_rev into the z half of dxz)
             dxz = torch.empty_like(xz)
@@ -569,7 +570,7 @@ class BiMambaInnerFn(torch.autograd.Function):
             K = cw32.shape[1]
             # in_proj
             dW_in = torch.mm(dxz.t(), x2)                                     # (2D, dm)
-            dx = torch.mm(dxz, Wi).view(Bsz, L, dm)
+            dx = gemm_nt(dxz, Wi.t().contiguous()).view(Bsz, L, dm)
             dA_log = dA * A32                                                 # A = -exp(A_log)
             dW_x = unpack_x_proj_grad(dW_xp, R, N)
         return (dx.to(xdt), dW_in.to(pdt[0]), dwb[:, :K].reshape(cw_shape).to(pdt[1]), dwb[:, K].to(pdt[2]),
