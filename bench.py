@@ -153,7 +153,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -234,8 +234,8 @@ def scan_sweep(bm, peak):
     """Config-5 points: single-direction selective_scan op, 524 288 frames, D=288, N=16."""
     out = []
     g = torch.Generator(device="cuda").manual_seed(0)
-    for dtype, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
-        for L in (256, 2048):
+    for dtype, name, Ls in ((torch.bfloat16, "bf16", (64, 256, 1024, 4096, 8192)), (torch.float32, "f32", (256, 2048))):
+        for L in Ls:
             Bsz = (1 << 19) // L
             u = torch.randn(Bsz, D_INNER, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
             delta = (0.5 * torch.randn(Bsz, D_INNER, L, device="cuda", generator=g)).to(dtype).requires_grad_(True)
@@ -385,14 +385,24 @@ def run_ours(args, rank, world, local_rank):
         fwd_ms = statistics.mean(times["scan_fwd"][N_LAYERS:])
         alg = scan_bytes(B * L, 2, 2, True)
         achieved = alg / (bwd_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "scan_traffic.json")
+        if os.path.exists(tpath) and (B, L) == (64, 201):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("scan_bwd_dram_bytes_per_launch"), tj.get("source")
         roofline = {
-            "kernel": "scan_bwd_kernel (both directions, one launch per layer)", "bound": "hbm",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "scan_bwd_kernel<bf16> (both directions, one launch per layer; the longest kernel of the step)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src, "avg_launch_ms": bwd_ms,
             "algorithmic_bytes_per_launch": alg,
-            "note": "bf16 IO, (7D+4N)*2 B per frame per direction (SURVEY 8d); config-2 tensors fit in the 126 MB L2 and "
-                    "the kernel is FP32-issue/MUFU bound (DESIGN.md), so the HBM fraction is low by construction; "
-                    "scan_fwd avg launch %.4f ms = %.1f GB/s" % (fwd_ms, scan_bytes(B * L, 2, 2, False) / (fwd_ms * 1e-3) / 1e9),
+            "note": "bf16 IO, (7D+4N)*2 B per frame per direction (SURVEY 8d) x 12864 frames x 2 directions.  The kernel is "
+                    "bound by instruction issue, not by HBM (DESIGN.md 4.2: ~490 SASS instructions per element at 37 %% issue "
+                    "utilisation; the config-2 working set also sits in the 126 MB L2), so the HBM fraction is low by "
+                    "construction.  scan_fwd (MUFU-bound, DESIGN.md 4.1) avg launch %.4f ms = %.1f GB/s algorithmic"
+                    % (fwd_ms, scan_bytes(B * L, 2, 2, False) / (fwd_ms * 1e-3) / 1e9),
+            "kernels_ms": {k: round(statistics.mean(v[len(v) // 3:]), 4) for k, v in times.items()},
         }
         sweep = None if args.no_sweep else scan_sweep(bm, peak)
         cpu = None
@@ -403,7 +413,8 @@ def run_ours(args, rank, world, local_rank):
             "steps": K, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args, world), l2="flushed between steps (256 MB write, untimed); per-step CUDA events summed",
-                           launch="CUDA-graph replay" if use_graph else "eager", state="fp32", weights="fp32 master, bf16 autocast"),
+                           launch="CUDA-graph replay" if use_graph else "eager", state="fp32", weights="fp32 master, bf16 autocast",
+                           gemm="tcgen05 (this repo)" if bm.ops.TC_GEMM else "cuBLAS"),
             "clocks": clocks,
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K,
