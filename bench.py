@@ -283,7 +283,18 @@ def run_ours(args, rank, world, local_rank):
         for layer in model.backbone_layers:
             layer.mamba.A_log.add_(0.1 * torch.randn_like(layer.mamba.A_log))
     params = list(model.backbone_layers.parameters())
-    bucket = bm.FlatGradBucket(params)
+    if world > 1:
+        bucket = bm.FlatGradBucket(params)      # one flat buffer -> one NCCL all-reduce per step
+        zero_grad = bucket.zero
+        all_reduce = bucket.all_reduce_mean
+    else:                                       # single GPU: no collective, so no bucket; autograd assigns .grad
+
+        def zero_grad():
+            for p in params:
+                p.grad = None
+
+        def all_reduce():
+            return None
     opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4, capturable=True, fused=True)
 
     B, L = args.batch, args.frames
@@ -298,30 +309,30 @@ def run_ours(args, rank, world, local_rank):
 
     use_graph = not args.no_graph
     if use_graph and world == 1:
-        runner = bm.GraphedTrainStep(fwd_loss, x_dev, bucket.zero, opt, warmup=3)
+        runner = bm.GraphedTrainStep(fwd_loss, x_dev, zero_grad, opt, warmup=3)
 
         def step(x=None):
             return runner.run(x)
     elif use_graph:
-        runner = bm.GraphedTrainStep(fwd_loss, x_dev, bucket.zero, None, warmup=3)
+        runner = bm.GraphedTrainStep(fwd_loss, x_dev, zero_grad, None, warmup=3)
 
         def step(x=None):
             loss = runner.run(x)
-            bucket.all_reduce_mean()
+            all_reduce()
             opt.step()
             return loss
     else:
         def step(x=None):
-            bucket.zero()
+            zero_grad()
             loss = fwd_loss(x_dev if x is None else x.cuda(non_blocking=True))
             loss.backward()
-            bucket.all_reduce_mean()
+            all_reduce()
             opt.step()
             return loss
 
     # count our own kernels in one eager step (the graph replays exactly these)
     bm._lib.launch_count = 0
-    bucket.zero()
+    zero_grad()
     fwd_loss(x_dev).backward()
     torch.cuda.synchronize()
     launches_per_step = bm._lib.launch_count
@@ -377,7 +388,7 @@ def run_ours(args, rank, world, local_rank):
         bm._lib.kernel_timer = timer
         for _ in range(3):
             flush.zero_()
-            bucket.zero()
+            zero_grad()
             fwd_loss(x_dev).backward()
         bm._lib.kernel_timer = None
         times = timer.summary()

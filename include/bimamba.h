@@ -155,6 +155,12 @@ int bimamba_reduce_partials(const float* part, void* out, int64_t groups, int64_
                             int64_t part_gs, int64_t row_stride, int64_t out_gs,
                             int out_dtype, int accumulate, bimamba_stream_t stream);
 
+/* Column sums of a (rows, cols) matrix with row stride ld (elements): the bias gradients of the Linear layers.
+ * Writes fp32 partials part (nslices, cols), nslices = bimamba_colsum_slices(rows); finish with
+ * bimamba_reduce_partials. */
+int bimamba_colsum_slices(int64_t rows);
+int bimamba_colsum(const void* x, float* part, int64_t rows, int cols, int64_t ld, int dtype, bimamba_stream_t stream);
+
 /* LayerNorm over the channel axis of a dense (rows, channels) matrix: the nn.LayerNorm(d_model) calls
  * of PN_BiMambas_Encoder (DualStreamSEMamba.py:458-459, :472, :482) and norm_f (:703, :759).
  * y = (x - mean) * rstd * gamma + beta, written in out_dtype (the dtype the following GEMM reads).

@@ -23,7 +23,7 @@ EXPORTS = (
     "bimamba_selective_scan_fwd", "bimamba_selective_scan_bwd",
     "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_conv_bwd_slices",
     "bimamba_reduce_partials", "bimamba_layernorm_fwd", "bimamba_layernorm_bwd_blocks", "bimamba_layernorm_bwd",
-    "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt",
+    "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_colsum_slices", "bimamba_colsum",
 )
 
 
@@ -98,6 +98,10 @@ def load() -> C.CDLL:
         lib.bimamba_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]
         lib.bimamba_gemm_nt_block_n.restype = i32
         lib.bimamba_gemm_nt_block_n.argtypes = [i32]
+        lib.bimamba_colsum_slices.restype = i32
+        lib.bimamba_colsum_slices.argtypes = [i64]
+        lib.bimamba_colsum.restype = i32
+        lib.bimamba_colsum.argtypes = [vp, vp, i64, i32, i64, i32, vp]
         lib.bimamba_gemm_nt_block_n_k.restype = i32
         lib.bimamba_gemm_nt_block_n_k.argtypes = [i32, i32]
         lib.bimamba_gemm_nt.restype = i32

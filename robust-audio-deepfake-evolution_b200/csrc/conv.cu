@@ -297,6 +297,33 @@ reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t gr
 }
 
 // time slots per batch row in the backward: enough threads to fill the GPU, few enough partials
+// Column sums of a (rows, cols) activation matrix (bias gradients of the Linear layers): stage 1 writes one fp32
+// partial row per slice of kColRows rows; bimamba_reduce_partials finishes the sum in fixed order.
+constexpr int kColRows = 256;
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, float* __restrict__ part, int64_t rows, int cols, int64_t ld) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const int64_t r0 = (int64_t)blockIdx.y * kColRows;
+  float s = 0.f;
+  if (col < cols) {
+#pragma unroll 4
+    for (int i = ry; i < kColRows; i += 8) {
+      const int64_t r = r0 + i;
+      if (r < rows) s += to_f(x[r * ld + col]);
+    }
+  }
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += sm[k][cx];
+    part[(int64_t)blockIdx.y * cols + col] = s;
+  }
+}
+
 static int conv_sy(int batch, int seqlen, int dim) {
   const int nseg = (seqlen + kSeg - 1) / kSeg;
   const int64_t per_slot = (int64_t)(batch < 1 ? 1 : batch) * ((dim + 3) / 4);
@@ -418,6 +445,23 @@ extern "C" int bimamba_reduce_partials(const float* part, void* out, int64_t gro
     reduce_kernel<8><<<nblocks(32), 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
   else
     reduce_kernel<32><<<nblocks(8), 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+extern "C" int bimamba_colsum_slices(int64_t rows) { return (int)((rows + kColRows - 1) / kColRows); }
+
+extern "C" int bimamba_colsum(const void* x, float* part, int64_t rows, int cols, int64_t ld, int dtype,
+                              bimamba_stream_t stream) {
+  if (rows == 0 || cols == 0) return 0;
+  if (!x || !part) { set_err("colsum: null operand"); return -1; }
+  if (rows < 0 || cols < 0 || dtype < 0 || dtype > 2) { set_err("colsum: bad sizes"); return -3; }
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)bimamba_colsum_slices(rows));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == BIMAMBA_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), part, rows, cols, ld);
+  else if (dtype == BIMAMBA_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), part, rows, cols, ld);
+  else colsum_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), part, rows, cols, ld);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .mamba_simple import Mamba
-from .ops import layer_norm_fn
+from .ops import feed_forward_fn, layer_norm_fn
 
 
 class PN_BiMambas_Encoder(nn.Module):
@@ -31,8 +31,10 @@ class PN_BiMambas_Encoder(nn.Module):
         x_norm = layer_norm_fn(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)               # :472
         mamba_out = self.mamba.forward_bidirectional(x_norm)                                         # :473-481 in one fused pass
         mamba_out = layer_norm_fn(mamba_out, self.norm2.weight, self.norm2.bias, self.norm2.eps)    # :482
-        ff_out = self.feed_forward(mamba_out)                    # :483
-        return ff_out + residual                                 # :485
+        if isinstance(self.feed_forward[1], nn.GELU) and self.feed_forward[1].approximate == "none":
+            l1, l2 = self.feed_forward[0], self.feed_forward[2]
+            return feed_forward_fn(mamba_out, l1.weight, l1.bias, l2.weight, l2.bias, residual=residual)   # :483-485
+        return self.feed_forward(mamba_out) + residual
 
 
 class BiMambaBackend(nn.Module):

@@ -388,6 +388,76 @@ def gemm_nt(A, B, bias=None, addend=None, out_dtype=None):
     return out
 
 
+def colsum(x2: torch.Tensor) -> torch.Tensor:
+    """Sum over the rows of a (rows, cols) matrix -> fp32 (cols): bias gradient of a Linear layer."""
+    lib = _lib.load()
+    rows, cols = x2.shape
+    out = torch.empty((cols,), device=x2.device, dtype=torch.float32)
+    if rows == 0:
+        return out.zero_()
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    nsl = lib.bimamba_colsum_slices(rows)
+    part = torch.empty((nsl, cols), device=x2.device, dtype=torch.float32)
+    with _timed("colsum"):
+        _lib.check(lib.bimamba_colsum(_ptr(x2), _ptr(part), rows, cols, x2.stride(0), _dt(x2), _stream()), "bimamba_colsum")
+    reduce_raw(part, out, groups=1, rows=nsl, cols=cols, part_gs=0, row_stride=cols, out_gs=0)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# feed-forward of the encoder layer: Linear(144, 576) -> GELU -> Linear(576, 144) (+ residual)
+# (DualStreamSEMamba.py:460-464, :483-485)
+# ----------------------------------------------------------------------------------------
+class FeedForwardFn(torch.autograd.Function):
+    """y = W2 gelu(W1 x + b1) + b2 (+ residual).  bf16 / fp16: both products and both data gradients run on the
+    tcgen05 GEMM with bias / residual in its epilogue; bias gradients are this repository's column-sum kernel."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, residual, cdtype):
+        _require_cuda(x, W1, b1, W2, b2, residual)
+        with torch.autocast("cuda", enabled=False):
+            shape = x.shape
+            x2 = x.detach().to(cdtype).reshape(-1, shape[-1])
+            if x2.stride(-1) != 1:
+                x2 = x2.contiguous()
+            W1c, W2c = W1.detach().to(cdtype), W2.detach().to(cdtype)
+            h = gemm_nt(x2, W1c, bias=_f32c(b1))                               # :461
+            a = torch.nn.functional.gelu(h)                                    # :462
+            res2 = None if residual is None else residual.detach().reshape(-1, W2.shape[0])
+            out_dtype = cdtype if residual is None else residual.dtype
+            y = gemm_nt(a, W2c, bias=_f32c(b2), addend=res2, out_dtype=out_dtype)   # :463, :485
+            if any(ctx.needs_input_grad):
+                ctx.save_for_backward(x2, h, a, W1c, W2c)
+                ctx.meta = (shape, x.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype, residual is not None)
+            return y.view(*shape[:-1], W2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, h, a, W1c, W2c = ctx.saved_tensors
+        shape, xdt, w1dt, b1dt, w2dt, b2dt, has_res = ctx.meta
+        with torch.autocast("cuda", enabled=False):
+            cd = x2.dtype
+            g = dy.reshape(-1, W2c.shape[0]).to(cd)
+            if g.stride(-1) != 1 or g.stride(0) != g.shape[1]:
+                g = g.contiguous()
+            db2 = colsum(g)
+            dW2 = torch.mm(g.t(), a)
+            da = gemm_nt(g, W2c.t().contiguous())
+            dh = torch.ops.aten.gelu_backward(da, h)
+            db1 = colsum(dh)
+            dW1 = torch.mm(dh.t(), x2)
+            dx = gemm_nt(dh, W1c.t().contiguous())
+        return (dx.view(shape).to(xdt), dW1.to(w1dt), db1.to(b1dt), dW2.to(w2dt), db2.to(b2dt),
+                dy if has_res else None, None)
+
+
+def feed_forward_fn(x, W1, b1, W2, b2, residual=None, compute_dtype=None):
+    if compute_dtype is None:
+        compute_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    return FeedForwardFn.apply(x, W1, b1, W2, b2, residual, compute_dtype)
+
+
 # ----------------------------------------------------------------------------------------
 # LayerNorm of the encoder layer (DualStreamSEMamba.py:472, :482, :759)
 # ----------------------------------------------------------------------------------------

@@ -212,3 +212,37 @@ def test_gemm_nt_strided_operand():
     W = (torch.randn(48, 288, generator=g) / 17).to(torch.bfloat16).cuda()
     out = bm.ops.gemm_nt(big[:, :288], W, out_dtype=torch.float32)
     assert rel(out, big[:, :288].double() @ W.double().t()) < 1e-5
+
+
+# ---------------------------------------------------------------- feed-forward + column sums
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_feed_forward_fn(dtype):
+    """Linear(144,576) -> GELU -> Linear(576,144) + residual (DualStreamSEMamba.py:460-464, :483-485) vs torch fp64."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 70, 144, generator=g)
+    res = torch.randn(3, 70, 144, generator=g)
+    W1 = torch.randn(576, 144, generator=g) / 12
+    b1 = torch.randn(576, generator=g) * 0.1
+    W2 = torch.randn(144, 576, generator=g) / 24
+    b2 = torch.randn(144, generator=g) * 0.1
+    cot = torch.randn(3, 70, 144, generator=g)
+    ref_in = [t.double().requires_grad_(True) for t in (x, W1, b1, W2, b2, res)]
+    xr, W1r, b1r, W2r, b2r, rr = ref_in
+    ref = torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(xr, W1r, b1r)), W2r, b2r) + rr
+    (ref * cot.double()).sum().backward()
+    dev_in = [t.cuda().requires_grad_(True) for t in (x, W1, b1, W2, b2, res)]
+    out = bm.ops.feed_forward_fn(dev_in[0], *dev_in[1:5], residual=dev_in[5], compute_dtype=dtype)
+    assert out.dtype == torch.float32                      # the residual stream stays fp32
+    out.backward(cot.cuda())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert rel(out, ref) < tol
+    for a, b in zip(dev_in, ref_in):
+        assert rel(a.grad, b.grad) < tol
+
+
+@pytest.mark.parametrize("rows,cols", [(12864, 576), (1, 7), (300, 144)])
+def test_colsum(rows, cols):
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, cols, generator=g).to(torch.bfloat16)
+    out = bm.ops.colsum(x.cuda())
+    assert rel(out, x.double().sum(0)) < 1e-5
