@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_
     if (ok) {
       const T* su = s_act + bf * nact * kT * G + tid;
       const int nvalid = L - c0 * kT;  // steps of this chunk that exist (>= 1)
-#pragma unroll 2
+#pragma unroll 4
       for (int i = 0; i < kT; ++i) {
         if ((i & (BIMAMBA_CKPT - 1)) == 0 && p.ckpt && i < nvalid) {  // state entering this 8-step chunk
           float4* ck = reinterpret_cast<float4*>(
