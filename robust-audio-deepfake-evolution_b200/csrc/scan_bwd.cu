@@ -8,19 +8,21 @@
 //
 // Mapping.  The backward needs h[t-1] and a[t] of every step while walking time in reverse, so a
 // thread cannot keep all 16 states of a channel for a whole chunk.  Instead
-//   * a thread owns a QUAD of states (2 x float2, so the recurrences issue as FMUL2 / FFMA2) of one
-//     channel: lane = 4 * channel_in_warp + quad, a warp works on 8 channels, a CTA (4 warps) on a
+//   * a thread owns a PAIR of states (one float2, so the recurrences issue as FMUL2 / FFMA2) of one
+//     channel: lane = 8 * channel_in_warp + pair, a warp works on 4 channels, a CTA (8 warps) on a
 //     "pass" of 32 channels and on `group_channels` = 32 * passes channels of one (batch, dir).
+//     The per-thread history (a[t], h[t]) and dB/dC accumulators are 4 x 8 float2 = 64 registers, which
+//     keeps the kernel under 128 registers: 16 warps per SM.
 //   * time is walked in 8-step chunks from the last to the first (8 = the forward's checkpoint
 //     interval).  Per (chunk, pass) the raw tiles (u, dout, z, ypre [8 x 32 channels], the chunk's
 //     B|C|dt_r rows and the 32 x 16 checkpoint tile) are staged by 16-byte cp.async into double
 //     buffers while the previous item computes: ONE block barrier per item.
-//   * the four lanes of a quad also split the chunk's 8 ELEMENTS of their channel two each: a lane
-//     computes delta (fused dt projection + softplus), delta*u, g and dz of its two elements once,
-//     the quad exchanges them by width-4 shuffles, and after the recurrence the 4-lane
-//     reduce-scatter of the n-sums lands exactly those two elements back on the lane that owns
-//     them, which finishes du / ddelta / dD / dbias - no shared-memory round trip, no extra barrier.
-//   * the chunk is re-run forward from its checkpoint keeping a[t], h[t] in 64 registers, then the
+//   * the eight lanes of a channel also own the chunk's 8 ELEMENTS of that channel, one each: a lane
+//     computes delta (fused dt projection + softplus), delta*u, g and dz of its element once, the
+//     octet exchanges them by width-8 shuffles, and after the recurrence the 8-lane reduce-scatter of
+//     the n-sums lands exactly that element back on the lane that owns it, which finishes du / ddelta
+//     / dD / dbias - no shared-memory round trip, no extra barrier.
+//   * the chunk is re-run forward from its checkpoint keeping a[t], h[t] in registers, then the
 //     reverse recurrence runs over the same registers - no (B, L, D, N) tensor, 16 exps per element.
 //   * dB/dC accumulate in registers over the passes of a chunk, then are summed over the CTA's 32
 //     (warp, channel) lanes in fixed order through shared memory and written as per-group partials;
@@ -34,35 +36,36 @@ namespace bimamba {
 #define BIMAMBA_BWD_MINB 2
 #endif
 constexpr int kBT = BIMAMBA_CKPT;          // steps per backward chunk == checkpoint interval (8)
-constexpr int kBW = 4;                     // warps per CTA
+constexpr int kBW = 8;                     // warps per CTA
 constexpr int kBThreads = kBW * 32;
-constexpr int kBC = 32;                    // channels per pass
+constexpr int kBC = 32;                    // channels per pass (4 per warp)
 constexpr int kMaxKP = 4;                  // passes per CTA: group_channels = 32 * passes
 constexpr int kNRaw = 5;                   // raw tiles: u, dout, z, ypre, delta
 constexpr int kRedStride = kBT * 2 * kN + 16;  // floats per (warp, channel) partial in the dB/dC reduction
 static_assert(kBC == 2 * kN, "the dB/dC column sum maps one thread column to one [dB|dC] column");
-static_assert(kBT == 8, "a quad of lanes owns 2 x 4 = 8 steps");
+static_assert(kBT == 8, "the 8 lanes of a channel own the 8 steps of a chunk");
+static_assert(kBThreads == kBT * 2 * kN, "one thread per [dB|dC] entry of a chunk in the column sum");
 
-// Sum over the 4 lanes of a quad of v[0..7]; lane q returns the totals of steps 2q and 2q+1.
-// Fixed tree -> deterministic.
-__device__ __forceinline__ void reduce_scatter4(const float (&v)[8], int q, float& r0, float& r1) {
-  const bool b1 = q & 2, b0 = q & 1;
+// Sum over the 8 lanes of an octet of v[0..7]; lane p returns the total of step p.  Fixed tree -> deterministic.
+__device__ __forceinline__ float reduce_scatter8(const float (&v)[8], int p) {
+  const bool b2 = p & 4, b1 = p & 2, b0 = p & 1;
   float w4[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float send = b1 ? v[i] : v[i + 4];
-    const float keep = b1 ? v[i + 4] : v[i];
-    w4[i] = keep + __shfl_xor_sync(kFull, send, 2);
+    const float send = b2 ? v[i] : v[i + 4];
+    const float keep = b2 ? v[i + 4] : v[i];
+    w4[i] = keep + __shfl_xor_sync(kFull, send, 4);
   }
   float w2[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const float send = b0 ? w4[i] : w4[i + 2];
-    const float keep = b0 ? w4[i + 2] : w4[i];
-    w2[i] = keep + __shfl_xor_sync(kFull, send, 1);
+    const float send = b1 ? w4[i] : w4[i + 2];
+    const float keep = b1 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(kFull, send, 2);
   }
-  r0 = w2[0];
-  r1 = w2[1];
+  const float send = b0 ? w2[0] : w2[1];
+  const float keep = b0 ? w2[1] : w2[0];
+  return keep + __shfl_xor_sync(kFull, send, 1);
 }
 
 template <typename T>
@@ -73,7 +76,7 @@ struct BwdSmem {
   static constexpr size_t raw_bytes = 2 * raw_elems * sizeof(T);
   static constexpr size_t xr_bytes = (size_t)kBT * kXW * sizeof(T);
   static constexpr size_t f32_floats = 2 * kBC * kN /*ckpt tiles*/ + kBT * kXW + 32 * kRedStride +
-                                       kMaxKP * kBC * (BIMAMBA_MAX_DT_RANK + 2 + 2 * kN + 2 * 4);
+                                       kMaxKP * kBC * (BIMAMBA_MAX_DT_RANK + 2 + 2 * kN + 2 * 8) + 3 * kBC * kBT;
   static constexpr size_t total = raw_bytes + xr_bytes + f32_floats * sizeof(float);
 };
 
@@ -86,8 +89,8 @@ __global__ void __launch_bounds__(kBThreads, BIMAMBA_BWD_MINB) scan_bwd_kernel(c
   const int b = blockIdx.z, dir = blockIdx.y, G = p.group_channels, g = blockIdx.x, d0 = g * G;
   const int KP = G / kBC;
   const int ngroups = gridDim.x;
-  const int warp = tid >> 5, lane = tid & 31, cw = lane >> 2, q = lane & 3;
-  const int rc = warp * 8 + cw;  // channel of this thread within a pass
+  const int warp = tid >> 5, lane = tid & 31, cw = lane >> 3, pr = lane & 7;
+  const int rc = warp * 4 + cw;  // channel of this thread within a pass
   const int L = p.seqlen, nsub = (L + kBT - 1) / kBT;
   const bool gated = p.z != nullptr, expl = p.delta != nullptr;
   const bool softplus = (p.flags & BIMAMBA_FLAG_SOFTPLUS) != 0;
@@ -122,7 +125,8 @@ __global__ void __launch_bounds__(kBThreads, BIMAMBA_BWD_MINB) scan_bwd_kernel(c
   float* s_D = s_bias + kMaxKP * kBC;                              // [G]
   float* s_m = s_D + kMaxKP * kBC;                                 // [G][16]  reverse carry a*dh
   float* s_dA = s_m + kMaxKP * kBC * kN;                           // [G][16]
-  float* s_acc = s_dA + kMaxKP * kBC * kN;                         // [2][4][G]: dD / dbias partial of (quad lane, channel)
+  float* s_acc = s_dA + kMaxKP * kBC * kN;                         // [2][G][8]: dD / dbias partial of (channel, octet lane)
+  float* s_el = s_acc + 2 * 8 * kMaxKP * kBC;                      // [3][kBC][8]: delta, delta*u, g of the item (step-major per channel)
 
   const bool dim_vec = (p.dim % kV) == 0 && (d0 % kV) == 0;
   const bool vec_u = dim_vec && aligned16(gu + d0) && (p.u_ts % kV) == 0;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(kBThreads, BIMAMBA_BWD_MINB) scan_bwd_kernel(c
           }
         }
       }
-      if (gck) {  // 32 channels x 16 states = 128 float4
+      if (gck && tid < kBC * kN / 4) {  // 32 channels x 16 states = 128 float4
         const int c = c_lo + (tid >> 2);
         const bool ok = c < col_end;
         cp_async16(sc + tid * 4, ok ? (gck + ((int64_t)c0 * p.dim + c) * kN + (tid & 3) * 4) : gck, ok);
@@ -222,19 +226,18 @@ __global__ void __launch_bounds__(kBThreads, BIMAMBA_BWD_MINB) scan_bwd_kernel(c
     s_m[e] = 0.f;
     s_dA[e] = 0.f;
   }
-  for (int e = tid; e < 2 * 4 * kMaxKP * kBC; e += kBThreads) s_acc[e] = 0.f;
+  for (int e = tid; e < 2 * 8 * kMaxKP * kBC; e += kBThreads) s_acc[e] = 0.f;
   if (!gck) {
     for (int e = tid; e < 2 * kBC * kN; e += kBThreads) s_ck[e] = 0.f;  // single chunk: the start state is zero
   }
 
-  float2 dBa[kBT][2], dCa[kBT][2];
+  float2 dBa[kBT], dCa[kBT];
 #pragma unroll
   for (int i = 0; i < kBT; ++i) {
-    dBa[i][0] = dBa[i][1] = make_float2(0.f, 0.f);
-    dCa[i][0] = dCa[i][1] = make_float2(0.f, 0.f);
+    dBa[i] = make_float2(0.f, 0.f);
+    dCa[i] = make_float2(0.f, 0.f);
   }
   const int R4 = (R + 3) >> 2;
-  const int pcc = tid & (kBC - 1);  // [dB|dC] column of this thread in the per-chunk column sum
 
   int item = 0;
   for (int c0 = nsub - 1; c0 >= 0; --c0) {
@@ -264,182 +267,160 @@ __global__ void __launch_bounds__(kBThreads, BIMAMBA_BWD_MINB) scan_bwd_kernel(c
       const int cg = k * kBC + rc;  // channel within the group
       const int c = d0 + cg;
       const bool okc = c < p.dim && cg < G;
-      const T* sr = s_raw + bf * SM::raw_elems + rc;
-      const float4 hs = *reinterpret_cast<const float4*>(s_ck + bf * kBC * kN + rc * kN + 4 * q);
+      const float2 hs = *reinterpret_cast<const float2*>(s_ck + bf * kBC * kN + rc * kN + 2 * pr);
 
-      // ---- this lane's two elements (steps 2q, 2q+1 of channel rc)
-      float e_u[2], e_dl[2], e_dlu[2], e_g[2], e_sp[2];
-      int64_t e_off[2];
-      {
-        const float bias = s_bias[cg];
+      // ---- this lane's element: step pr of channel rc
+      float e_u = 0.f, e_dl = 0.f, e_dlu = 0.f, e_g = 0.f, e_sp = 0.f;
+      const int tau_e = tau0 + pr;
+      const bool live = okc && tau_e < L;
+      const int64_t e_off = (int64_t)(dir ? (L - 1 - tau_e) : tau_e) * p.out_ts + c;
+      if (live) {
+        const T* sr = s_raw + bf * SM::raw_elems + pr * RS + rc;
+        e_u = to_f(sr[0]);
+        const float dov = to_f(sr[kBT * RS]);
+        float draw = s_bias[cg];
+        if (expl) {
+          draw += to_f(sr[4 * kBT * RS]);
+        } else {
+          const float4* xr = reinterpret_cast<const float4*>(s_xf + pr * kXW + 2 * kN);
+          const float4* wr = reinterpret_cast<const float4*>(s_wdt + cg * BIMAMBA_MAX_DT_RANK);
+          float2 acc0 = make_float2(draw, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int i = 2 * q + j;
-          const int tau = tau0 + i;
-          float dl = 0.f, dlu = 0.f, gg = 0.f, uu = 0.f, sp = 0.f;
-          const int64_t t = dir ? (L - 1 - tau) : tau;
-          e_off[j] = t * p.out_ts + c;
-          if (okc && tau < L) {
-            uu = to_f(sr[i * RS]);
-            const float dov = to_f(sr[(kBT + i) * RS]);
-            float draw = bias;
-            if (expl) {
-              draw += to_f(sr[(4 * kBT + i) * RS]);
-            } else {
-              const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW + 2 * kN);
-              const float4* wr = reinterpret_cast<const float4*>(s_wdt + cg * BIMAMBA_MAX_DT_RANK);
-              float2 acc0 = make_float2(draw, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll
-              for (int r4 = 0; r4 < 4; ++r4) {
-                if (r4 < R4) {
-                  const float4 x = xr[r4], w = wr[r4];
-                  acc0 = __ffma2_rn(make_float2(w.x, w.y), make_float2(x.x, x.y), acc0);
-                  acc1 = __ffma2_rn(make_float2(w.z, w.w), make_float2(x.z, x.w), acc1);
-                }
-              }
-              draw = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-            }
-            if (softplus) {
-              dl = softplus_f(draw);
-              sp = draw > 20.f ? 1.f : sigmoid_f(draw);
-            } else {
-              dl = draw;
-              sp = 1.f;
-            }
-            dlu = dl * uu;
-            gg = dov;
-            if (gated) {
-              const float zz = to_f(sr[(2 * kBT + i) * RS]);
-              const float sg = sigmoid_f(zz);
-              gg = dov * zz * sg;
-              if (need_yp) {
-                const float yp = to_f(sr[(3 * kBT + i) * RS]);
-                gdz[e_off[j]] = from_f<T>(dov * yp * sg * (1.f + zz * (1.f - sg)));
-              }
+          for (int r4 = 0; r4 < 4; ++r4) {
+            if (r4 < R4) {
+              const float4 x = xr[r4], w = wr[r4];
+              acc0 = __ffma2_rn(make_float2(w.x, w.y), make_float2(x.x, x.y), acc0);
+              acc1 = __ffma2_rn(make_float2(w.z, w.w), make_float2(x.z, x.w), acc1);
             }
           }
-          e_u[j] = uu;
-          e_dl[j] = dl;
-          e_dlu[j] = dlu;
-          e_g[j] = gg;
-          e_sp[j] = sp;
+          draw = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+        }
+        if (softplus) {
+          e_dl = softplus_f(draw);
+          e_sp = draw > 20.f ? 1.f : sigmoid_f(draw);
+        } else {
+          e_dl = draw;
+          e_sp = 1.f;
+        }
+        e_dlu = e_dl * e_u;
+        e_g = dov;
+        if (gated) {
+          const float zz = to_f(sr[2 * kBT * RS]);
+          const float sg = sigmoid_f(zz);
+          e_g = dov * zz * sg;
+          if (need_yp) {
+            const float yp = to_f(sr[3 * kBT * RS]);
+            gdz[e_off] = from_f<T>(dov * yp * sg * (1.f + zz * (1.f - sg)));
+          }
         }
       }
-      // quad exchange: every lane gets delta, delta*u, g of all 8 steps of its channel
-      float dq[kBT], uq[kBT], gq[kBT];
-#pragma unroll
-      for (int i = 0; i < kBT; ++i) {
-        dq[i] = __shfl_sync(kFull, e_dl[i & 1], i >> 1, 4);
-        uq[i] = __shfl_sync(kFull, e_dlu[i & 1], i >> 1, 4);
-        gq[i] = __shfl_sync(kFull, e_g[i & 1], i >> 1, 4);
-      }
 
-      // ---- recurrence: this thread owns states 4q..4q+3 of channel rc of the pass
-      float4 A4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (okc) A4 = __ldg(reinterpret_cast<const float4*>(p.A + (int64_t)c * kN) + q);
-      const float2 A2a = make_float2(A4.x * kLog2e, A4.y * kLog2e), A2b = make_float2(A4.z * kLog2e, A4.w * kLog2e);
+      // ---- recurrence: this thread owns states 2*pr, 2*pr+1 of channel rc of the pass; delta, delta*u and g of
+      // the channel's 8 steps are exchanged inside the warp through 3 x 32 floats of shared memory
+      // (one STS each, then LDS.128 broadcasts: cheaper on the shared-memory pipe than 40 shuffles)
+      s_el[rc * kBT + pr] = e_dl;
+      s_el[(kBC + rc) * kBT + pr] = e_dlu;
+      s_el[(2 * kBC + rc) * kBT + pr] = e_g;
+      __syncwarp();
+      const float4* pdl = reinterpret_cast<const float4*>(s_el + rc * kBT);
+      const float4* pdu = reinterpret_cast<const float4*>(s_el + (kBC + rc) * kBT);
+      const float4* pgg = reinterpret_cast<const float4*>(s_el + (2 * kBC + rc) * kBT);
+      float2 A2 = make_float2(0.f, 0.f);
+      if (okc) {
+        const float2 Av = __ldg(reinterpret_cast<const float2*>(p.A + (int64_t)c * kN) + pr);
+        A2 = make_float2(Av.x * kLog2e, Av.y * kLog2e);
+      }
       // re-run the chunk forward from the checkpoint, keeping a[t], h[t]
-      float2 a[kBT][2], hh[kBT][2];
+      float2 a[kBT], hh[kBT];
       {
-        float2 h0 = make_float2(hs.x, hs.y), h1 = make_float2(hs.z, hs.w);
+        float2 h = hs;
+        const float4 d0v = pdl[0], d1v = pdl[1], u0v = pdu[0], u1v = pdu[1];
+        const float dq[kBT] = {d0v.x, d0v.y, d0v.z, d0v.w, d1v.x, d1v.y, d1v.z, d1v.w};
+        const float uq[kBT] = {u0v.x, u0v.y, u0v.z, u0v.w, u1v.x, u1v.y, u1v.z, u1v.w};
 #pragma unroll
         for (int i = 0; i < kBT; ++i) {
-          const float4 B4 = *reinterpret_cast<const float4*>(s_xf + i * kXW + 4 * q);
-          const float2 dd = make_float2(dq[i], dq[i]), uu = make_float2(uq[i], uq[i]);
-          const float2 x0 = __fmul2_rn(dd, A2a), x1 = __fmul2_rn(dd, A2b);
-          a[i][0] = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-          a[i][1] = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
-          h0 = __ffma2_rn(a[i][0], h0, __fmul2_rn(uu, make_float2(B4.x, B4.y)));
-          h1 = __ffma2_rn(a[i][1], h1, __fmul2_rn(uu, make_float2(B4.z, B4.w)));
-          hh[i][0] = h0;
-          hh[i][1] = h1;
+          const float di = dq[i], ui = uq[i];
+          const float2 B2 = *reinterpret_cast<const float2*>(s_xf + i * kXW + 2 * pr);
+          const float2 x = __fmul2_rn(make_float2(di, di), A2);
+          a[i] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          h = __ffma2_rn(a[i], h, __fmul2_rn(make_float2(ui, ui), B2));
+          hh[i] = h;
         }
       }
       // reverse recurrence:  dh_i = g_i C_i + m_{i+1},  m_i = a_i dh_i
-      float4* pm = reinterpret_cast<float4*>(s_m + cg * kN + 4 * q);
-      const float4 m4 = *pm;
-      float2 m0 = make_float2(m4.x, m4.y), m1 = make_float2(m4.z, m4.w);
-      float2 dA0 = make_float2(0.f, 0.f), dA1 = make_float2(0.f, 0.f);
+      float2* pm = reinterpret_cast<float2*>(s_m + cg * kN + 2 * pr);
+      float2 m = *pm;
+      float2 dA2 = make_float2(0.f, 0.f);
       float vA[kBT], vU[kBT];
+      const float4 d0r = pdl[0], d1r = pdl[1], u0r = pdu[0], u1r = pdu[1], g0r = pgg[0], g1r = pgg[1];
+      const float dr[kBT] = {d0r.x, d0r.y, d0r.z, d0r.w, d1r.x, d1r.y, d1r.z, d1r.w};
+      const float ur[kBT] = {u0r.x, u0r.y, u0r.z, u0r.w, u1r.x, u1r.y, u1r.z, u1r.w};
+      const float gr[kBT] = {g0r.x, g0r.y, g0r.z, g0r.w, g1r.x, g1r.y, g1r.z, g1r.w};
 #pragma unroll
       for (int i = kBT - 1; i >= 0; --i) {
-        const float4 B4 = *reinterpret_cast<const float4*>(s_xf + i * kXW + 4 * q);
-        const float4 C4 = *reinterpret_cast<const float4*>(s_xf + i * kXW + kN + 4 * q);
-        const float2 gg = make_float2(gq[i], gq[i]), dd = make_float2(dq[i], dq[i]), uu = make_float2(uq[i], uq[i]);
-        const float2 dh0 = __ffma2_rn(gg, make_float2(C4.x, C4.y), m0);
-        const float2 dh1 = __ffma2_rn(gg, make_float2(C4.z, C4.w), m1);
-        m0 = __fmul2_rn(a[i][0], dh0);
-        m1 = __fmul2_rn(a[i][1], dh1);
-        const float2 hp0 = (i == 0) ? make_float2(hs.x, hs.y) : hh[i == 0 ? 0 : i - 1][0];
-        const float2 hp1 = (i == 0) ? make_float2(hs.z, hs.w) : hh[i == 0 ? 0 : i - 1][1];
-        const float2 da0 = __fmul2_rn(m0, hp0), da1 = __fmul2_rn(m1, hp1);
-        dA0 = __ffma2_rn(da0, dd, dA0);
-        dA1 = __ffma2_rn(da1, dd, dA1);
-        dBa[i][0] = __ffma2_rn(dh0, uu, dBa[i][0]);
-        dBa[i][1] = __ffma2_rn(dh1, uu, dBa[i][1]);
-        dCa[i][0] = __ffma2_rn(gg, hh[i][0], dCa[i][0]);
-        dCa[i][1] = __ffma2_rn(gg, hh[i][1], dCa[i][1]);
-        const float2 ta = __ffma2_rn(da1, A2b, __fmul2_rn(da0, A2a));
-        const float2 tu = __ffma2_rn(dh1, make_float2(B4.z, B4.w), __fmul2_rn(dh0, make_float2(B4.x, B4.y)));
+        const float di = dr[i], ui = ur[i], gi = gr[i];
+        const float2 B2 = *reinterpret_cast<const float2*>(s_xf + i * kXW + 2 * pr);
+        const float2 C2 = *reinterpret_cast<const float2*>(s_xf + i * kXW + kN + 2 * pr);
+        const float2 gg = make_float2(gi, gi);
+        const float2 dh = __ffma2_rn(gg, C2, m);
+        m = __fmul2_rn(a[i], dh);
+        const float2 hp = (i == 0) ? hs : hh[i == 0 ? 0 : i - 1];
+        const float2 da = __fmul2_rn(m, hp);
+        dA2 = __ffma2_rn(da, make_float2(di, di), dA2);
+        dBa[i] = __ffma2_rn(dh, make_float2(ui, ui), dBa[i]);
+        dCa[i] = __ffma2_rn(gg, hh[i], dCa[i]);
+        const float2 ta = __fmul2_rn(da, A2);
+        const float2 tu = __fmul2_rn(dh, B2);
         vA[i] = ta.x + ta.y;   // sum_n dh a h[t-1] A (x log2e; scaled back below)
         vU[i] = tu.x + tu.y;   // sum_n dh B
       }
-      *pm = make_float4(m0.x, m0.y, m1.x, m1.y);
+      *pm = m;
       {
-        float4* pa = reinterpret_cast<float4*>(s_dA + cg * kN + 4 * q);
-        float4 acc = *pa;
-        acc.x += dA0.x;
-        acc.y += dA0.y;
-        acc.z += dA1.x;
-        acc.w += dA1.y;
+        float2* pa = reinterpret_cast<float2*>(s_dA + cg * kN + 2 * pr);
+        float2 acc = *pa;
+        acc.x += dA2.x;
+        acc.y += dA2.y;
         *pa = acc;
       }
-      float rA[2], rU[2];
-      reduce_scatter4(vA, q, rA[0], rA[1]);
-      reduce_scatter4(vU, q, rU[0], rU[1]);
+      const float rA = reduce_scatter8(vA, pr);
+      const float rU = reduce_scatter8(vU, pr);
 
-      // ---- finish this lane's two elements: du, ddelta, dD, dbias
+      // ---- finish this lane's element: du, ddelta, dD, dbias
       {
-        const float Dd = s_D[cg];
         float dDl = 0.f, dbl = 0.f;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (okc && tau0 + 2 * q + j < L) {
-            dDl = fmaf(e_g[j], e_u[j], dDl);
-            const float duv = fmaf(e_g[j], Dd, e_dl[j] * rU[j]);
-            const float ddl = fmaf(e_u[j], rU[j], rA[j] * kLn2) * e_sp[j];
-            dbl += ddl;
-            gdu[e_off[j]] = from_f<T>(duv);
-            gdd[e_off[j]] = from_f<T>(ddl);
-          }
+        if (live) {
+          dDl = e_g * e_u;
+          const float duv = fmaf(e_g, s_D[cg], e_dl * rU);
+          dbl = fmaf(e_u, rU, rA * kLn2) * e_sp;
+          gdu[e_off] = from_f<T>(duv);
+          gdd[e_off] = from_f<T>(dbl);
         }
-        s_acc[q * (kMaxKP * kBC) + cg] += dDl;   // this thread is the only writer of these two slots
-        s_acc[(4 + q) * (kMaxKP * kBC) + cg] += dbl;
+        s_acc[cg * 8 + pr] += dDl;   // this thread is the only writer of these two slots
+        s_acc[(kMaxKP * kBC + cg) * 8 + pr] += dbl;
       }
     }  // passes
 
     // ---- dB/dC of this chunk: sum over the CTA's 32 (warp, channel) lanes in fixed order
     {
-      float* my = s_red + (warp * 8 + cw) * kRedStride;
+      float* my = s_red + (warp * 4 + cw) * kRedStride;
 #pragma unroll
       for (int i = 0; i < kBT; ++i) {
-        *reinterpret_cast<float4*>(my + i * 2 * kN + 4 * q) = make_float4(dBa[i][0].x, dBa[i][0].y, dBa[i][1].x, dBa[i][1].y);
-        *reinterpret_cast<float4*>(my + i * 2 * kN + kN + 4 * q) = make_float4(dCa[i][0].x, dCa[i][0].y, dCa[i][1].x, dCa[i][1].y);
-        dBa[i][0] = dBa[i][1] = make_float2(0.f, 0.f);
-        dCa[i][0] = dCa[i][1] = make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(my + i * 2 * kN + 2 * pr) = dBa[i];
+        *reinterpret_cast<float2*>(my + i * 2 * kN + kN + 2 * pr) = dCa[i];
+        dBa[i] = make_float2(0.f, 0.f);
+        dCa[i] = make_float2(0.f, 0.f);
       }
     }
     __syncthreads();  // (2)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int i = (tid >> 5) + j * kBW;
+    {
+      const int i = tid >> 5, col = tid & 31;   // one thread per [dB|dC] entry of the chunk
       const int tau = tau0 + i;
       if (tau < L) {
         float s = 0.f;
 #pragma unroll 8
-        for (int w = 0; w < 32; ++w) s += s_red[w * kRedStride + i * 2 * kN + pcc];
+        for (int w = 0; w < 32; ++w) s += s_red[w * kRedStride + i * 2 * kN + col];
         const int64_t t = dir ? (L - 1 - tau) : tau;
-        partB[t * pb_ts + pcc] = s;
+        partB[t * pb_ts + col] = s;
       }
     }
     // the next item's barrier (1) orders these reads before s_red is rewritten
@@ -451,15 +432,15 @@ __global__ void __launch_bounds__(kBThreads, BIMAMBA_BWD_MINB) scan_bwd_kernel(c
     const int c = d0 + e / kN;
     if (c < p.dim) p.dA_part[(bd * p.dim + c) * kN + (e % kN)] = s_dA[e];
   }
-  // dD / dbias: the 4 lanes of a quad share a channel; combine in fixed order
+  // dD / dbias: the 8 lanes of an octet share a channel; combine in fixed order
   for (int cg = tid; cg < G; cg += kBThreads) {
     const int c = d0 + cg;
     if (c < p.dim) {
       float sD = 0.f, sb = 0.f;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        sD += s_acc[w * (kMaxKP * kBC) + cg];
-        sb += s_acc[(4 + w) * (kMaxKP * kBC) + cg];
+      for (int w = 0; w < 8; ++w) {
+        sD += s_acc[cg * 8 + w];
+        sb += s_acc[(kMaxKP * kBC + cg) * 8 + w];
       }
       if (p.dD_part) p.dD_part[bd * p.dim + c] = sD;
       if (p.dbias_part) p.dbias_part[bd * p.dim + c] = sb;
