@@ -189,6 +189,20 @@ int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void
                     const float* bias, const void* addend, int64_t M, int N, int K, int in_dtype, int out_dtype,
                     bimamba_stream_t stream);
 
+/* Per-step weight preparation of one Mamba block in one launch: from the fp32 master parameters
+ * (mamba_block.py:22-39) to the arrangements the kernels read, in `dtype`:
+ *   Wi (2D, dm) = in_proj.weight; WiT (dm, 2D) its transpose; Wxp (48, D) = x_proj.weight repacked
+ *   [B | C | dt_r | 0]; WxpT (D, 48); Wo2 (dm, ndir*D) = [out_proj.weight] x ndir; WoT (D, dm);
+ *   WdT (16, D) = dt_proj.weight^T zero padded; A (D, N) fp32 = -exp(A_log) (mamba_block.py:82). */
+int bimamba_pack_weights(const float* W_in, const float* W_x, const float* W_dt, const float* A_log,
+                         const float* W_out, void* Wi, void* WiT, void* Wxp, void* WxpT, void* Wo2,
+                         void* WoT, void* WdT, float* A, int d_model, int d_inner, int d_state,
+                         int dt_rank, int ndir, int dtype, bimamba_stream_t stream);
+
+/* dst (rows, cols) = cast(src); dstT (cols, rows) = cast(src)^T: a Linear weight and its data-gradient operand. */
+int bimamba_cast_transpose(const float* src, void* dst, void* dstT, int rows, int cols, int dtype,
+                           bimamba_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ EXPORTS = (
     "bimamba_selective_scan_fwd", "bimamba_selective_scan_bwd",
     "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_conv_bwd_slices",
     "bimamba_reduce_partials", "bimamba_layernorm_fwd", "bimamba_layernorm_bwd_blocks", "bimamba_layernorm_bwd",
-    "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_colsum_slices", "bimamba_colsum",
+    "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_colsum_slices", "bimamba_colsum", "bimamba_pack_weights", "bimamba_cast_transpose",
 )
 
 
@@ -98,6 +98,10 @@ def load() -> C.CDLL:
         lib.bimamba_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]
         lib.bimamba_gemm_nt_block_n.restype = i32
         lib.bimamba_gemm_nt_block_n.argtypes = [i32]
+        lib.bimamba_pack_weights.restype = i32
+        lib.bimamba_pack_weights.argtypes = [vp] * 13 + [i32] * 6 + [vp]
+        lib.bimamba_cast_transpose.restype = i32
+        lib.bimamba_cast_transpose.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         lib.bimamba_colsum_slices.restype = i32
         lib.bimamba_colsum_slices.argtypes = [i64]
         lib.bimamba_colsum.restype = i32

@@ -421,33 +421,34 @@ class FeedForwardFn(torch.autograd.Function):
             x2 = x.detach().to(cdtype).reshape(-1, shape[-1])
             if x2.stride(-1) != 1:
                 x2 = x2.contiguous()
-            W1c, W2c = W1.detach().to(cdtype), W2.detach().to(cdtype)
+            W1c, W1T = cast_transpose(W1.detach(), cdtype)
+            W2c, W2T = cast_transpose(W2.detach(), cdtype)
             h = gemm_nt(x2, W1c, bias=_f32c(b1))                               # :461
             a = torch.nn.functional.gelu(h)                                    # :462
             res2 = None if residual is None else residual.detach().reshape(-1, W2.shape[0])
             out_dtype = cdtype if residual is None else residual.dtype
             y = gemm_nt(a, W2c, bias=_f32c(b2), addend=res2, out_dtype=out_dtype)   # :463, :485
             if any(ctx.needs_input_grad):
-                ctx.save_for_backward(x2, h, a, W1c, W2c)
+                ctx.save_for_backward(x2, h, a, W1T, W2T)
                 ctx.meta = (shape, x.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype, residual is not None)
             return y.view(*shape[:-1], W2.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x2, h, a, W1c, W2c = ctx.saved_tensors
+        x2, h, a, W1T, W2T = ctx.saved_tensors
         shape, xdt, w1dt, b1dt, w2dt, b2dt, has_res = ctx.meta
         with torch.autocast("cuda", enabled=False):
             cd = x2.dtype
-            g = dy.reshape(-1, W2c.shape[0]).to(cd)
+            g = dy.reshape(-1, W2T.shape[1]).to(cd)
             if g.stride(-1) != 1 or g.stride(0) != g.shape[1]:
                 g = g.contiguous()
             db2 = colsum(g)
             dW2 = torch.mm(g.t(), a)
-            da = gemm_nt(g, W2c.t().contiguous())
+            da = gemm_nt(g, W2T)
             dh = torch.ops.aten.gelu_backward(da, h)
             db1 = colsum(dh)
             dW1 = torch.mm(dh.t(), x2)
-            dx = gemm_nt(dh, W1c.t().contiguous())
+            dx = gemm_nt(dh, W1T)
         return (dx.view(shape).to(xdt), dW1.to(w1dt), db1.to(b1dt), dW2.to(w2dt), db2.to(b2dt),
                 dy if has_res else None, None)
 
@@ -523,6 +524,42 @@ def layer_norm_fn(x, weight, bias, eps=1e-5, out_dtype=None):
 # ----------------------------------------------------------------------------------------
 # the fused block: both directions, shared weights
 # ----------------------------------------------------------------------------------------
+def pack_weights(W_in, W_x, W_dt, A_log, W_out, ndir: int, dtype):
+    """One launch: fp32 master parameters -> (Wi, WiT, Wxp, WxpT, Wo2, WoT, WdT) in `dtype` and A = -exp(A_log) fp32
+    (layouts in include/bimamba.h: bimamba_pack_weights)."""
+    lib = _lib.load()
+    D2, dm = W_in.shape
+    D = D2 // 2
+    N = A_log.shape[1]
+    R = W_dt.shape[1]
+    sizes = (D2 * dm, D2 * dm, XW * D, XW * D, dm * ndir * D, D * dm, MAX_DT_RANK * D)
+    flat = torch.empty((sum(sizes),), device=W_in.device, dtype=dtype)
+    shapes = ((D2, dm), (dm, D2), (XW, D), (D, XW), (dm, ndir * D), (D, dm), (MAX_DT_RANK, D))
+    outs, off = [], 0
+    for n_, sh in zip(sizes, shapes):       # every size is a multiple of 8 elements -> 16-byte aligned views
+        outs.append(flat[off:off + n_].view(sh))
+        off += n_
+    A32 = torch.empty((D, N), device=W_in.device, dtype=torch.float32)
+    srcs = [_f32c(t) for t in (W_in, W_x, W_dt, A_log, W_out)]
+    with _timed("pack"):
+        _lib.check(lib.bimamba_pack_weights(*[_ptr(t) for t in srcs], *[_ptr(t) for t in outs], _ptr(A32),
+                                            dm, D, N, R, ndir, _DT[dtype], _stream()), "bimamba_pack_weights")
+    return (*outs, A32)
+
+
+def cast_transpose(W: torch.Tensor, dtype):
+    """fp32 (rows, cols) weight -> (W in dtype, W^T in dtype) with one launch."""
+    lib = _lib.load()
+    rows, cols = W.shape
+    src = _f32c(W)
+    dst = torch.empty((rows, cols), device=W.device, dtype=dtype)
+    dstT = torch.empty((cols, rows), device=W.device, dtype=dtype)
+    with _timed("pack"):
+        _lib.check(lib.bimamba_cast_transpose(_ptr(src), _ptr(dst), _ptr(dstT), rows, cols, _DT[dtype], _stream()),
+                   "bimamba_cast_transpose")
+    return dst, dstT
+
+
 def pack_x_proj(W_x: torch.Tensor, R: int, N: int, dtype) -> torch.Tensor:
     """x_proj.weight (R + 2N, D) -> (48, D): rows [B | C | dt_r | 0] so one GEMM emits the row layout the
     scan kernels stage with aligned vector copies (mamba_block.py:73-75 splits [dt_r | B | C])."""
@@ -565,14 +602,11 @@ class BiMambaInnerFn(torch.autograd.Function):
             ndir = 2 if bidirectional else 1
             M = Bsz * L
             dev = x.device
-            Wi = W_in.detach().to(cdtype)
-            Wxp = pack_x_proj(W_x.detach(), R, N, cdtype)
-            Wo = W_out.detach().to(cdtype)
-            Wo2 = torch.cat([Wo] * ndir, dim=1) if ndir > 1 else Wo           # (dm, ndir*D)
+            Wi, WiT, Wxp, WxpT, Wo2, WoT, WdT, A32 = pack_weights(W_in.detach(), W_x.detach(), W_dt.detach(),
+                                                                  A_log.detach(), W_out.detach(), ndir, cdtype)
             Wd32 = _f32c(W_dt)
             cw32 = _f32c(conv_w).reshape(D, -1)
             cb32 = _f32c(conv_b)
-            A32 = -torch.exp(A_log.detach().float())
             D32, bdt32 = _f32c(Dp), _f32c(b_dt)
 
             x2 = x.detach().to(cdtype).reshape(M, dm)
@@ -589,7 +623,7 @@ class BiMambaInnerFn(torch.autograd.Function):
                                          dtr_padded=True)                     # :80-120, :61
             out = gemm_nt(rows2d(y).view(M, ndir * D), Wo2).view(Bsz, L, dm)  # :62 + DualStreamSEMamba.py:481
             if needs_bwd:
-                ctx.save_for_backward(x2, xz, xc, xdbl, y, Wi, Wxp, Wd32, Wo, cw32, cb32, A32, D32, bdt32,
+                ctx.save_for_backward(x2, xz, xc, xdbl, y, WiT, WxpT, WoT, WdT, Wd32, cw32, cb32, A32, D32, bdt32,
                                       ckpt if ckpt is not None else torch.empty(0), ypre)
                 ctx.meta = (Bsz, L, ndir, R, x.dtype,
                             tuple(t.dtype for t in (W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out)),
@@ -598,7 +632,7 @@ class BiMambaInnerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        (x2, xz, xc, xdbl, y, Wi, Wxp, Wd32, Wo, cw32, cb32, A32, D32, bdt32, ckpt, ypre) = ctx.saved_tensors
+        (x2, xz, xc, xdbl, y, WiT, WxpT, WoT, WdT, Wd32, cw32, cb32, A32, D32, bdt32, ckpt, ypre) = ctx.saved_tensors
         Bsz, L, ndir, R, xdt, pdt, cw_shape = ctx.meta
         ckpt = ckpt if ckpt.numel() else None
         with torch.autocast("cuda", enabled=False):
@@ -612,7 +646,7 @@ class BiMambaInnerFn(torch.autograd.Function):
 
             g2 = dout.to(cd).reshape(M, dm)
             # out_proj
-            dy = gemm_nt(g2, Wo.t().contiguous())                             # (M, D), shared by both directions
+            dy = gemm_nt(g2, WoT)                                             # (M, D), shared by both directions
             y2 = rows2d(y).view(M, ndir * D)
             dW_out2 = torch.mm(g2.t(), y2)                                    # (dm, ndir*D)
             dW_out = dW_out2[:, :D] + dW_out2[:, D:] if ndir > 1 else dW_out2
@@ -623,15 +657,13 @@ class BiMambaInnerFn(torch.autograd.Function):
                 A32, D32, bdt32, True, dyb, ckpt, ypre, dtr_padded=True)
             # dt_proj (weight gradient in fp32; the data gradient joins the x_proj row)
             dd2 = rows2d(ddelta)                                              # (M*ndir, D)
-            WdT_pad = torch.zeros((XW - 2 * N, D), device=dd2.device, dtype=cd)
-            WdT_pad[:R] = Wd32.t()
-            dxdbl = torch.cat([rows2d(dbc), gemm_nt(dd2, WdT_pad)], dim=1)    # (M*ndir, 48) [dB | dC | ddt_r | 0]
+            dxdbl = torch.cat([rows2d(dbc), gemm_nt(dd2, WdT)], dim=1)        # (M*ndir, 48) [dB | dC | ddt_r | 0]
             dW_dt = torch.mm(dd2.t(), xdbl)[:, 2 * N:2 * N + R]               # (D, R); full-row GEMM: a 9-column strided
                                                                               # operand would fall off cuBLAS's fast kernels
             # x_proj
             xc2 = rows2d(xc)
             dW_xp = torch.mm(dxdbl.t(), xc2)                                  # (48, D)
-            dxc = gemm_nt(dxdbl, Wxp.t().contiguous(), addend=rows2d(du))     # (M*ndir, D)
+            dxc = gemm_nt(dxdbl, WxpT, addend=rows2d(du))                     # (M*ndir, D)
             dxc4 = dxc.view(Bsz, L, ndir, D).permute(0, 2, 1, 3)
             # conv (writes dx into the x half and dz_fwd + dz_rev into the z half of dxz)
             dxz = torch.empty_like(xz)
@@ -640,7 +672,7 @@ class BiMambaInnerFn(torch.autograd.Function):
             K = cw32.shape[1]
             # in_proj
             dW_in = torch.mm(dxz.t(), x2)                                     # (2D, dm)
-            dx = gemm_nt(dxz, Wi.t().contiguous()).view(Bsz, L, dm)
+            dx = gemm_nt(dxz, WiT).view(Bsz, L, dm)
             dA_log = dA * A32                                                 # A = -exp(A_log)
             dW_x = unpack_x_proj_grad(dW_xp, R, N)
         return (dx.to(xdt), dW_in.to(pdt[0]), dwb[:, :K].reshape(cw_shape).to(pdt[1]), dwb[:, K].to(pdt[2]),
