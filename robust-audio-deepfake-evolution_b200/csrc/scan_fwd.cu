@@ -20,9 +20,13 @@
 //   * direction 1 walks the same storage back to front (t = L-1-step): flip(M(flip(x))) of
 //     src/models/DualStreamSEMamba.py:476-478 with no flipped copy; both directions are
 //     blockIdx.y of the same launch.
+//   * small problems (fewer than ~16 warps per SM of channel lanes) use the two-lanes-per-channel variant in
+//     scan_fwd2.cu: same math, twice the warps.
 //   * training forward also writes the fp32 state entering every 8-step chunk ("checkpoints",
 //     (B, dir, chunk, D, 16): 64 contiguous bytes per thread) and the pre-gate y; the backward
 //     recomputes the states of a chunk from its checkpoint (no (B, L, D, N) tensor).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bimamba {
@@ -220,6 +224,7 @@ static void launch_fwd(const bimamba_scan_desc* d, cudaStream_t st) {
 }
 
 int check_desc(const bimamba_scan_desc* d, bool bwd);  // api.cu
+void launch_fwd_pair(const bimamba_scan_desc* d, cudaStream_t st);  // scan_fwd2.cu
 
 }  // namespace bimamba
 
@@ -232,10 +237,20 @@ extern "C" int bimamba_selective_scan_fwd(const bimamba_scan_desc* d, bimamba_st
   const int G = d->group_channels;
   if (G < 32 || G > kFwdMaxThreads || (G & 31)) { set_err("forward group_channels must be 32, 64, 96 or 128 (use bimamba_scan_plan)"); return -5; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (d->io_dtype) {
-    case BIMAMBA_F32: launch_fwd<float>(d, st); break;
-    case BIMAMBA_BF16: launch_fwd<__nv_bfloat16>(d, st); break;
-    default: launch_fwd<__half>(d, st); break;
+  // One lane per channel is the cheaper instruction stream; with fewer than ~16 warps per SM of such lanes
+  // (the Phase-6 shapes: 36 864 rows) the two-lanes-per-channel variant hides latency better (measured:
+  // 0.097 vs 0.115 ms at batch 64 x 201 frames, 1.59 vs 1.12 ms at 2048 x 256).
+  const int64_t lanes = (int64_t)d->batch * d->ndir * d->dim;
+  const char* force = getenv("BIMAMBA_FWD_LANES");   // tuning experiments only
+  const bool pair = force ? atoi(force) == 2 : lanes < (int64_t)148 * 16 * 32;
+  if (pair) {
+    launch_fwd_pair(d, st);
+  } else {
+    switch (d->io_dtype) {
+      case BIMAMBA_F32: launch_fwd<float>(d, st); break;
+      case BIMAMBA_BF16: launch_fwd<__nv_bfloat16>(d, st); break;
+      default: launch_fwd<__half>(d, st); break;
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }

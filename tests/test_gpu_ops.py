@@ -246,3 +246,14 @@ def test_colsum(rows, cols):
     x = torch.randn(rows, cols, generator=g).to(torch.bfloat16)
     out = bm.ops.colsum(x.cuda())
     assert rel(out, x.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("lanes", ["1", "2"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scan_forward_variants(lanes, dtype, monkeypatch):
+    """Both forward kernels (one lane per channel - large problems; two lanes per channel - small problems) are
+    forced in turn on the same inputs; the size-based dispatch must not change results beyond rounding."""
+    monkeypatch.setenv("BIMAMBA_FWD_LANES", lanes)
+    for L, D in ((201, 288), (37, 40), (499, 17)):
+        errs = _run_both(2, D, L, dtype, seed=L + D)
+        assert max(errs.values()) < TOL[dtype], (lanes, L, D, errs)
