@@ -123,142 +123,141 @@ conv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const floa
   }
 }
 
-// Backward.  Thread = (batch b, time slot y, channel vector v); it walks the segments
-// s = y, y+SY, ... of its row (SY = time slots per batch row, conv_sy()).  For a segment [t0, t0+kSeg):
-//   pre_dir[t] = bias + sum_k w[k] x[t -/+ (H-k)];  g_dir[t] = dout_dir[t] * silu'(pre_dir[t])
-//   dx[tau]    = sum_k w[k] ( g_0[tau+H-k] + g_1[tau-H+k] )
-//   dw[k]     += sum_t g_0[t] x[t-H+k] + g_1[t] x[t+H-k];   dbias += sum_t g_0[t] + g_1[t]
-// (dw / dbias over the thread's OWN positions only; halo positions are recomputed for dx.)
-template <typename T, int V, int K>
+// Backward, tiled through shared memory.  A CTA owns a tile of kBwdT time steps x kBwdC channels of one batch
+// row: it stages x (T + 4H rows) and both directions' dout (T + 2H rows) with 16-byte cp.async - every load of
+// the tile is in flight at once - converts them in place to
+//   g_dir[t] = dout_dir[t] * silu'(bias + sum_k w[k] x[t -/+ (H-k)])
+// and then every thread (one channel, half of the tile's steps) forms
+//   dx[tau]  = sum_k w[k] ( g_0[tau+H-k] + g_1[tau-H+k] )
+//   dw[k]   += sum_t g_0[t] x[t-H+k] + g_1[t] x[t+H-k];   dbias += sum_t g_0[t] + g_1[t]
+// from shared memory.  dw / dbias leave as one partial row per CTA (fixed-order reduction afterwards); the sum
+// of the two directions' gate gradients dz is folded into the same pass (global -> global, coalesced).
+constexpr int kBwdT = 16;
+constexpr int kBwdC = 64;
+
+template <typename T, int K>
 __global__ void __launch_bounds__(kConvThreads)
-conv_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                const T* __restrict__ dout, T* __restrict__ dx, const T* __restrict__ dz_in, T* __restrict__ dz_out,
-                float* __restrict__ part, int batch, int ndir, int dim, int L, int SY, int64_t x_bs, int64_t x_ts,
-                int64_t g_bs, int64_t g_ds, int64_t g_ts, int64_t dx_bs, int64_t dx_ts, int silu) {
-  const int nvec = (dim + V - 1) / V;
-  const int nseg = (L + kSeg - 1) / kSeg;
-  const int64_t total = (int64_t)batch * SY * nvec;
-  const int64_t gid = (int64_t)blockIdx.x * kConvThreads + threadIdx.x;
-  if (gid >= total) return;
-  const int v = (int)(gid % nvec);
-  const int y = (int)((gid / nvec) % SY);
-  const int b = (int)(gid / ((int64_t)nvec * SY));
-  const int d = v * V;
+conv_bwd_tile_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     const T* __restrict__ dout, T* __restrict__ dx, const T* __restrict__ dz_in, T* __restrict__ dz_out,
+                     float* __restrict__ part, int batch, int ndir, int dim, int L, int64_t x_bs, int64_t x_ts,
+                     int64_t g_bs, int64_t g_ds, int64_t g_ts, int64_t dx_bs, int64_t dx_ts, int silu, int vec) {
   constexpr int H = K - 1;
+  constexpr int XR = kBwdT + 4 * H, GR = kBwdT + 2 * H;   // rows of the x and g tiles
+  constexpr int kV = 16 / sizeof(T);
+  __shared__ __align__(16) T s_xraw[XR * kBwdC];
+  __shared__ __align__(16) T s_graw[2 * GR * kBwdC];
+  __shared__ float s_x[XR * kBwdC];
+  __shared__ float s_g[2 * GR * kBwdC];
+  __shared__ float s_part[2][kBwdC][K + 1];
 
-  float wk[V][K], bs[V], dwl[V][K], dbl[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      wk[i][k] = __ldg(w + (int64_t)(d + i) * K + k);
-      dwl[i][k] = 0.f;
+  const int tid = threadIdx.x;
+  const int nct = (dim + kBwdC - 1) / kBwdC, ntt = (L + kBwdT - 1) / kBwdT;
+  const int ct = blockIdx.x % nct, tt = (blockIdx.x / nct) % ntt, b = blockIdx.x / (nct * ntt);
+  const int c0 = ct * kBwdC, t0 = tt * kBwdT;
+  const T* xb = x + (int64_t)b * x_bs;
+  const T* gb = dout + (int64_t)b * g_bs;
+
+  // ---- stage: x rows [t0-2H, t0+T+2H), g rows [t0-H, t0+T+H) of both directions (zero outside [0, L) x [0, dim))
+  if (vec) {
+    constexpr int VPR = kBwdC / kV;
+    for (int e = tid; e < XR * VPR; e += kConvThreads) {
+      const int r = e / VPR, v = e - r * VPR;
+      const int t = t0 - 2 * H + r, c = c0 + v * kV;
+      const bool ok = t >= 0 && t < L && c < dim;
+      cp_async16(s_xraw + r * kBwdC + v * kV, ok ? xb + (int64_t)t * x_ts + c : xb, ok);
     }
-    bs[i] = bias ? __ldg(bias + d + i) : 0.f;
-    dbl[i] = 0.f;
+    for (int e = tid; e < 2 * GR * VPR; e += kConvThreads) {
+      const int dsel = e / (GR * VPR), rr = e - dsel * GR * VPR;
+      const int r = rr / VPR, v = rr - r * VPR;
+      const int t = t0 - H + r, c = c0 + v * kV;
+      const bool ok = t >= 0 && t < L && c < dim && dsel < ndir;
+      cp_async16(s_graw + (dsel * GR + r) * kBwdC + v * kV, ok ? gb + (int64_t)dsel * g_ds + (int64_t)t * g_ts + c : gb, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  } else {
+    for (int e = tid; e < XR * kBwdC; e += kConvThreads) {
+      const int r = e / kBwdC, cc = e - r * kBwdC;
+      const int t = t0 - 2 * H + r, c = c0 + cc;
+      s_xraw[e] = (t >= 0 && t < L && c < dim) ? xb[(int64_t)t * x_ts + c] : from_f<T>(0.f);
+    }
+    for (int e = tid; e < 2 * GR * kBwdC; e += kConvThreads) {
+      const int dsel = e / (GR * kBwdC), rr = e - dsel * GR * kBwdC;
+      const int r = rr / kBwdC, cc = rr - r * kBwdC;
+      const int t = t0 - H + r, c = c0 + cc;
+      s_graw[e] = (t >= 0 && t < L && c < dim && dsel < ndir) ? gb[(int64_t)dsel * g_ds + (int64_t)t * g_ts + c] : from_f<T>(0.f);
+    }
   }
-  const T* xb = x + (int64_t)b * x_bs + d;
-  const T* gb = dout + (int64_t)b * g_bs + d;
-  T* dxb = dx + (int64_t)b * dx_bs + d;
+  __syncthreads();
+  for (int e = tid; e < XR * kBwdC; e += kConvThreads) s_x[e] = to_f(s_xraw[e]);
+  __syncthreads();
 
-  for (int s = y; s < nseg; s += SY) {
-    const int t0 = s * kSeg;
-    // Walk tau = t0-H .. t0+kSeg+H-1.  At each tau we have the x window xw[j] = x[tau-H+j] (j=0..2H),
-    // form g0[tau], g1[tau], and scatter them into the dx accumulators of the positions they touch:
-    //   g0[tau] contributes w[k] g0[tau] to dx[tau-H+k];   g1[tau] contributes w[k] g1[tau] to dx[tau+H-k]
-    // dx accumulators form a sliding window acc[j] = dx[tau-H+j], j = 0..2H; dx[tau-H] is complete
-    // once tau has been processed (g0 reaches back H, g1 reaches forward H).
-    float xw[2 * H + 1][V], acc[2 * H + 1][V];
+  // ---- g_dir = dout_dir * silu'(pre_dir) for every staged g row (row r <-> time t0-H+r <-> x row r+H)
+  {
+    const int cc = tid % kBwdC;
+    const int c = c0 + cc;
+    float wk[K], bs = 0.f;
 #pragma unroll
-    for (int j = 0; j < 2 * H + 1; ++j)
+    for (int k = 0; k < K; ++k) wk[k] = c < dim ? __ldg(w + (int64_t)c * K + k) : 0.f;
+    if (bias && c < dim) bs = __ldg(bias + c);
+    for (int r = tid / kBwdC; r < GR; r += kConvThreads / kBwdC) {
+      float g0 = to_f(s_graw[r * kBwdC + cc]), g1 = to_f(s_graw[(GR + r) * kBwdC + cc]);
+      if (silu) {
+        float p0 = bs, p1 = bs;
 #pragma unroll
-      for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 2 * H; ++j) {
-      const int t = t0 - 2 * H + j;
-      if (t >= 0 && t < L) {
-        load_row<T, V>(xb + (int64_t)t * x_ts, xw[j + 1]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < V; ++i) xw[j + 1][i] = 0.f;
+        for (int k = 0; k < K; ++k) {
+          p0 = fmaf(wk[k], s_x[(r + H - H + k) * kBwdC + cc], p0);      // x[t-H+k], t = t0-H+r -> x row r+k
+          p1 = fmaf(wk[k], s_x[(r + 2 * H - k) * kBwdC + cc], p1);      // x[t+H-k]              -> x row r+2H-k
+        }
+        g0 *= silu_grad(p0);
+        g1 *= silu_grad(p1);
       }
+      s_g[r * kBwdC + cc] = g0;
+      s_g[(GR + r) * kBwdC + cc] = g1;
     }
+    __syncthreads();
+
+    // ---- dx, dw, dbias: thread = (channel cc, half hs of the tile's steps)
+    const int hs = tid / kBwdC;
+    float dwl[K], dbl = 0.f;
 #pragma unroll
-    for (int s_ = 0; s_ < kSeg + 2 * H; ++s_) {
-      const int tau = t0 - H + s_;
+    for (int k = 0; k < K; ++k) dwl[k] = 0.f;
+    T* dxb = dx + (int64_t)b * dx_bs;
+    constexpr int SPT = kBwdT / (kConvThreads / kBwdC);   // steps per thread
+    for (int i = hs * SPT; i < (hs + 1) * SPT; ++i) {
+      const int tau = t0 + i;
+      if (tau >= L) break;
+      // g rows: time tau <-> row i+H;  x rows: time tau <-> row i+2H
+      float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 2 * H; ++j)
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          xw[j][i] = xw[j + 1][i];
-          acc[j][i] = acc[j + 1][i];
-        }
-#pragma unroll
-      for (int i = 0; i < V; ++i) acc[2 * H][i] = 0.f;
-      const int tn = tau + H;
-      if (tn >= 0 && tn < L) {
-        load_row<T, V>(xb + (int64_t)tn * x_ts, xw[2 * H]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < V; ++i) xw[2 * H][i] = 0.f;
+      for (int k = 0; k < K; ++k) {
+        acc = fmaf(wk[k], s_g[(i + H + H - k) * kBwdC + cc], acc);          // g_0[tau+H-k]
+        acc = fmaf(wk[k], s_g[(GR + i + H - H + k) * kBwdC + cc], acc);     // g_1[tau-H+k]
       }
-      if (tau >= 0 && tau < L) {
-        float g0[V], g1[V];
-        load_row<T, V>(gb + (int64_t)tau * g_ts, g0);
-        if (ndir > 1) {
-          load_row<T, V>(gb + g_ds + (int64_t)tau * g_ts, g1);
-        } else {
+      const float g0 = s_g[(i + H) * kBwdC + cc], g1 = s_g[(GR + i + H) * kBwdC + cc];
+      dbl += g0 + g1;
 #pragma unroll
-          for (int i = 0; i < V; ++i) g1[i] = 0.f;
-        }
-        const bool own = tau >= t0 && tau < t0 + kSeg;
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          if (silu) {
-            float p0 = bs[i], p1 = bs[i];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-              p0 = fmaf(wk[i][k], xw[k][i], p0);
-              p1 = fmaf(wk[i][k], xw[2 * H - k][i], p1);
-            }
-            g0[i] *= silu_grad(p0);
-            g1[i] *= silu_grad(p1);
-          }
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            acc[k][i] = fmaf(wk[i][k], g0[i], acc[k][i]);                  // dx[tau-H+k]
-            acc[2 * H - k][i] = fmaf(wk[i][k], g1[i], acc[2 * H - k][i]);  // dx[tau+H-k]
-          }
-          if (own) {
-            dbl[i] += g0[i] + g1[i];
-#pragma unroll
-            for (int k = 0; k < K; ++k) dwl[i][k] += g0[i] * xw[k][i] + g1[i] * xw[2 * H - k][i];
-          }
-        }
-      }
-      // dx[tau-H] is complete (for positions inside this segment)
-      const int td = tau - H;
-      if (td >= t0 && td < t0 + kSeg && td < L) {
-        store_row<T, V>(dxb + (int64_t)td * dx_ts, acc[0]);
+      for (int k = 0; k < K; ++k)
+        dwl[k] += g0 * s_x[(i + 2 * H - H + k) * kBwdC + cc] + g1 * s_x[(i + 2 * H + H - k) * kBwdC + cc];
+      if (c < dim) {
+        dxb[(int64_t)tau * dx_ts + c] = from_f<T>(acc);
         if (dz_in) {
-          float z0[V], z1[V];
-          load_row<T, V>(dz_in + (int64_t)b * g_bs + (int64_t)td * g_ts + d, z0);
-          if (ndir > 1) {
-            load_row<T, V>(dz_in + (int64_t)b * g_bs + g_ds + (int64_t)td * g_ts + d, z1);
-#pragma unroll
-            for (int i = 0; i < V; ++i) z0[i] += z1[i];
-          }
-          store_row<T, V>(dz_out + (int64_t)b * dx_bs + (int64_t)td * dx_ts + d, z0);
+          const T* zi = dz_in + (int64_t)b * g_bs + (int64_t)tau * g_ts + c;
+          float zz = to_f(zi[0]);
+          if (ndir > 1) zz += to_f(zi[g_ds]);
+          dz_out[(int64_t)b * dx_bs + (int64_t)tau * dx_ts + c] = from_f<T>(zz);
         }
       }
     }
-  }
-  float* o = part + ((int64_t)(b * SY + y) * dim + d) * (K + 1);
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
+    for (int k = 0; k < K; ++k) s_part[hs][cc][k] = dwl[k];
+    s_part[hs][cc][K] = dbl;
+    __syncthreads();
+    if (hs == 0 && c < dim) {
+      float* o = part + ((int64_t)(b * ntt + tt) * dim + c) * (K + 1);
 #pragma unroll
-    for (int k = 0; k < K; ++k) o[i * (K + 1) + k] = dwl[i][k];
-    o[i * (K + 1) + K] = dbl[i];
+      for (int k = 0; k <= K; ++k) o[k] = s_part[0][cc][k] + s_part[1][cc][k];
+    }
   }
 }
 
@@ -296,7 +295,6 @@ reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t gr
   }
 }
 
-// time slots per batch row in the backward: enough threads to fill the GPU, few enough partials
 // Column sums of a (rows, cols) activation matrix (bias gradients of the Linear layers): stage 1 writes one fp32
 // partial row per slice of kColRows rows; bimamba_reduce_partials finishes the sum in fixed order.
 constexpr int kColRows = 256;
@@ -324,13 +322,7 @@ colsum_kernel(const T* __restrict__ x, float* __restrict__ part, int64_t rows, i
   }
 }
 
-static int conv_sy(int batch, int seqlen, int dim) {
-  const int nseg = (seqlen + kSeg - 1) / kSeg;
-  const int64_t per_slot = (int64_t)(batch < 1 ? 1 : batch) * ((dim + 3) / 4);
-  int64_t sy = (150000 + per_slot - 1) / per_slot;
-  if (sy > nseg) sy = nseg;
-  return (int)(sy < 1 ? 1 : sy);
-}
+static int conv_bwd_time_tiles(int seqlen) { return seqlen > 0 ? (seqlen + kBwdT - 1) / kBwdT : 1; }
 
 template <typename T, int V>
 static void launch_conv_fwd(const void* x, const float* w, const float* bias, void* out, int batch, int ndir, int dim,
@@ -348,23 +340,22 @@ static void launch_conv_fwd(const void* x, const float* w, const float* bias, vo
   }
 }
 
-template <typename T, int V>
+template <typename T>
 static void launch_conv_bwd(const void* x, const float* w, const float* bias, const void* dout, void* dx,
                             const void* dz_in, void* dz_out, float* part, int batch, int ndir, int dim, int L, int width,
                             int64_t x_bs, int64_t x_ts, int64_t g_bs, int64_t g_ds, int64_t g_ts, int64_t dx_bs,
-                            int64_t dx_ts, int silu, cudaStream_t st) {
-  const int nvec = (dim + V - 1) / V, SY = conv_sy(batch, L, dim);
-  const int64_t total = (int64_t)batch * SY * nvec;
-  const unsigned blocks = (unsigned)((total + kConvThreads - 1) / kConvThreads);
+                            int64_t dx_ts, int silu, int vec, cudaStream_t st) {
+  const int nct = (dim + kBwdC - 1) / kBwdC, ntt = conv_bwd_time_tiles(L);
+  const unsigned blocks = (unsigned)((int64_t)batch * ntt * nct);
   const T* xp = reinterpret_cast<const T*>(x);
   const T* gp = reinterpret_cast<const T*>(dout);
   const T* zi = reinterpret_cast<const T*>(dz_in);
   T* dxp = reinterpret_cast<T*>(dx);
   T* zo = reinterpret_cast<T*>(dz_out);
   switch (width) {
-    case 2: conv_bwd_kernel<T, V, 2><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, SY, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu); break;
-    case 3: conv_bwd_kernel<T, V, 3><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, SY, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu); break;
-    default: conv_bwd_kernel<T, V, 4><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, SY, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu); break;
+    case 2: conv_bwd_tile_kernel<T, 2><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
+    case 3: conv_bwd_tile_kernel<T, 3><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
+    default: conv_bwd_tile_kernel<T, 4><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
   }
 }
 
@@ -403,7 +394,10 @@ extern "C" int bimamba_causal_conv1d_fwd(const void* x, const float* weight, con
   return 0;
 }
 
-extern "C" int bimamba_conv_bwd_slices(int batch, int seqlen, int dim) { return batch * conv_sy(batch, seqlen, dim); }
+extern "C" int bimamba_conv_bwd_slices(int batch, int seqlen, int dim) {
+  (void)dim;
+  return batch * conv_bwd_time_tiles(seqlen);
+}
 
 extern "C" int bimamba_causal_conv1d_bwd(const void* x, const float* weight, const float* bias, const void* dout, void* dx,
                                          const void* dz_in, void* dz_out, float* dwb_part, int batch, int ndir, int dim,
@@ -417,11 +411,14 @@ extern "C" int bimamba_causal_conv1d_bwd(const void* x, const float* weight, con
   if (ndir < 1 || ndir > 2 || dtype < 0 || dtype > 2 || batch < 0 || dim < 1 || seqlen < 0) { set_err("conv bwd: bad sizes"); return -3; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int silu = flags & BIMAMBA_FLAG_SILU;
-  const bool v4 = vec4_ok(dtype, dim, {x, dout, dx, dz_in, dz_out}, {x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts});
-#define CONV_BWD(T, V) launch_conv_bwd<T, V>(x, weight, bias, dout, dx, dz_in, dz_out, dwb_part, batch, ndir, dim, seqlen, width, x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts, silu, st)
-  if (dtype == BIMAMBA_F32) { if (v4) CONV_BWD(float, 4); else CONV_BWD(float, 1); }
-  else if (dtype == BIMAMBA_BF16) { if (v4) CONV_BWD(__nv_bfloat16, 4); else CONV_BWD(__nv_bfloat16, 1); }
-  else { if (v4) CONV_BWD(__half, 4); else CONV_BWD(__half, 1); }
+  // 16-byte cp.async staging needs 16-byte aligned rows of x and dout (dx / dz are written element-wise)
+  const int ev = dtype == BIMAMBA_F32 ? 4 : 8;
+  const int vec = (dim % ev == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(dout) % 16 == 0) &&
+                  (x_bs % ev == 0) && (x_ts % ev == 0) && (dout_bs % ev == 0) && (dout_ds % ev == 0) && (dout_ts % ev == 0);
+#define CONV_BWD(T) launch_conv_bwd<T>(x, weight, bias, dout, dx, dz_in, dz_out, dwb_part, batch, ndir, dim, seqlen, width, x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts, silu, vec, st)
+  if (dtype == BIMAMBA_F32) CONV_BWD(float);
+  else if (dtype == BIMAMBA_BF16) CONV_BWD(__nv_bfloat16);
+  else CONV_BWD(__half);
 #undef CONV_BWD
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
