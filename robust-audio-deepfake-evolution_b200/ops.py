@@ -80,6 +80,43 @@ def _timed(name: str):
     return _NULL if t is None else t(name)
 
 
+# ----------------------------------------------------------------------------------------
+# fork / join on a side stream: the weight-gradient GEMMs and bias column sums of a backward are independent of
+# the data-gradient chain, and at the Phase-6 sizes every kernel is too small to fill 148 SMs, so they run
+# concurrently (under CUDA-graph capture the fork/join becomes parallel graph branches).
+# ----------------------------------------------------------------------------------------
+_SIDE = {}
+SIDE_STREAM = os.environ.get("BIMAMBA_SIDE_STREAM", "1") != "0"
+
+
+class _Fork:
+    """with _Fork() as f: ... work enqueued on the side stream ...;  f.join() makes the current stream wait for it.
+    Tensors touched on the side stream must stay referenced until join() (callers join before returning)."""
+
+    def __enter__(self):
+        self.cur = torch.cuda.current_stream()
+        if not SIDE_STREAM:
+            self.side = None
+            return self
+        dev = self.cur.device_index
+        if dev not in _SIDE:
+            _SIDE[dev] = torch.cuda.Stream(device=dev)
+        self.side = _SIDE[dev]
+        self.side.wait_stream(self.cur)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.side is not None:
+            self.ctx.__exit__(*a)
+        return False
+
+    def join(self):
+        if self.side is not None:
+            self.cur.wait_stream(self.side)
+
+
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return None if t is None else t.detach().to(torch.float32).contiguous()
 
@@ -442,13 +479,17 @@ class FeedForwardFn(torch.autograd.Function):
             g = dy.reshape(-1, W2T.shape[1]).to(cd)
             if g.stride(-1) != 1 or g.stride(0) != g.shape[1]:
                 g = g.contiguous()
-            db2 = colsum(g)
-            dW2 = torch.mm(g.t(), a)
+            with _Fork() as f2:                       # second Linear's parameter gradients || its data gradient
+                db2 = colsum(g)
+                dW2 = torch.mm(g.t(), a)
             da = gemm_nt(g, W2T)
             dh = torch.ops.aten.gelu_backward(da, h)
-            db1 = colsum(dh)
-            dW1 = torch.mm(dh.t(), x2)
+            f2.join()
+            with _Fork() as f1:                       # first Linear's parameter gradients || its data gradient
+                db1 = colsum(dh)
+                dW1 = torch.mm(dh.t(), x2)
             dx = gemm_nt(dh, W1T)
+            f1.join()
         return (dx.view(shape).to(xdt), dW1.to(w1dt), db1.to(b1dt), dW2.to(w2dt), db2.to(b2dt),
                 dy if has_res else None, None)
 
@@ -646,10 +687,11 @@ class BiMambaInnerFn(torch.autograd.Function):
 
             g2 = dout.to(cd).reshape(M, dm)
             # out_proj
-            dy = gemm_nt(g2, WoT)                                             # (M, D), shared by both directions
             y2 = rows2d(y).view(M, ndir * D)
-            dW_out2 = torch.mm(g2.t(), y2)                                    # (dm, ndir*D)
-            dW_out = dW_out2[:, :D] + dW_out2[:, D:] if ndir > 1 else dW_out2
+            with _Fork() as f_out:                                            # out_proj weight gradient || dy, scan
+                dW_out2 = torch.mm(g2.t(), y2)                                # (dm, ndir*D)
+                dW_out = dW_out2[:, :D] + dW_out2[:, D:] if ndir > 1 else dW_out2
+            dy = gemm_nt(g2, WoT)                                             # (M, D), shared by both directions
             # scan (both directions in one launch); dy and z are broadcast over the direction axis
             dyb = dy.view(Bsz, 1, L, D).expand(Bsz, ndir, L, D)
             du, ddelta, dz, dbc, dA, dD, dbdt = scan_bwd_raw(
@@ -658,11 +700,12 @@ class BiMambaInnerFn(torch.autograd.Function):
             # dt_proj (weight gradient in fp32; the data gradient joins the x_proj row)
             dd2 = rows2d(ddelta)                                              # (M*ndir, D)
             dxdbl = torch.cat([rows2d(dbc), gemm_nt(dd2, WdT)], dim=1)        # (M*ndir, 48) [dB | dC | ddt_r | 0]
-            dW_dt = torch.mm(dd2.t(), xdbl)[:, 2 * N:2 * N + R]               # (D, R); full-row GEMM: a 9-column strided
-                                                                              # operand would fall off cuBLAS's fast kernels
-            # x_proj
             xc2 = rows2d(xc)
-            dW_xp = torch.mm(dxdbl.t(), xc2)                                  # (48, D)
+            with _Fork() as f_w:                                              # dt_proj / x_proj weight gradients || dxc, conv
+                dW_dt = torch.mm(dd2.t(), xdbl)[:, 2 * N:2 * N + R]           # (D, R); full-row GEMM: a 9-column strided
+                                                                              # operand would fall off cuBLAS's fast kernels
+                dW_xp = torch.mm(dxdbl.t(), xc2)                              # (48, D)
+            # x_proj
             dxc = gemm_nt(dxdbl, WxpT, addend=rows2d(du))                     # (M*ndir, D)
             dxc4 = dxc.view(Bsz, L, ndir, D).permute(0, 2, 1, 3)
             # conv (writes dx into the x half and dz_fwd + dz_rev into the z half of dxz)
@@ -671,9 +714,13 @@ class BiMambaInnerFn(torch.autograd.Function):
             dwb = conv_bwd_raw(xs, cw32, cb32, dxc4, dxz3[:, :, :D], True, dz_in=dz, dz_out=dxz3[:, :, D:])
             K = cw32.shape[1]
             # in_proj
-            dW_in = torch.mm(dxz.t(), x2)                                     # (2D, dm)
+            with _Fork() as f_in:                                             # in_proj weight gradient || its data gradient
+                dW_in = torch.mm(dxz.t(), x2)                                 # (2D, dm)
             dx = gemm_nt(dxz, WiT).view(Bsz, L, dm)
             dA_log = dA * A32                                                 # A = -exp(A_log)
+            f_out.join()
+            f_w.join()
+            f_in.join()
             dW_x = unpack_x_proj_grad(dW_xp, R, N)
         return (dx.to(xdt), dW_in.to(pdt[0]), dwb[:, :K].reshape(cw_shape).to(pdt[1]), dwb[:, K].to(pdt[2]),
                 dW_x.to(pdt[3]), dW_dt.to(pdt[4]), dbdt.to(pdt[5]), dA_log.to(pdt[6]), dD.to(pdt[7]),
