@@ -280,6 +280,165 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ---- persistent, warp-specialised variant --------------------------------------------------------------
+// One CTA per SM walks the (M tile, N tile) list with a static stride.  Roles: warp 0 = TMA producer over a
+// 4-stage shared-memory ring that runs ahead across tiles; warp 1 = MMA issuer alternating between TWO TMEM
+// accumulators; warps 2-5 = epilogue (each owns the TMEM lane quarter warp % 4): they drain accumulator j
+// (TMEM -> registers -> padded shared tile -> row-contiguous global stores) while the MMAs of tile j+1 run, so
+// load, tensor-core and store phases of consecutive tiles overlap inside one CTA.
+constexpr int kPStages = 4;
+constexpr int kPEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kPThreads = 64 + 32 * kPEpiWarps;
+
+template <typename TOut>
+__global__ void __launch_bounds__(kPThreads, 1)
+gemm_nt_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       TOut* __restrict__ C, const float* __restrict__ bias, const TOut* __restrict__ addend, int M,
+                       int N, int K, int64_t ldc, int block_n, uint32_t idesc, uint32_t tmem_cols, uint32_t acc_stride) {
+  extern __shared__ __align__(1024) unsigned char gsm[];
+  __shared__ __align__(8) uint64_t full_bar[kPStages], empty_bar[kPStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + kGK - 1) / kGK;
+  const int ntm = (M + kGM - 1) / kGM, ntn = (N + block_n - 1) / block_n;
+  const int ntiles = ntm * ntn;
+  const uint32_t a_bytes = kGM * kGK * 2, b_bytes = (uint32_t)block_n * kGK * 2;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+  unsigned char* base = gsm + ((1024u - (smem_u32(gsm) & 1023u)) & 1023u);
+  unsigned char* tile = base + (size_t)kPStages * stage_bytes;   // epilogue staging tile (after the ring)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&acc_full[j], 1);
+      mbar_init(&acc_empty[j], kPEpiWarps);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t / ntn) * kGM, n0 = (t % ntn) * block_n;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % kPStages, ph = (it / kPStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          unsigned char* sa = base + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+          tma_load_2d(sa, &map_a, &full_bar[s], kb * kGK, m0);
+          tma_load_2d(sa + a_bytes, &map_b, &full_bar[s], kb * kGK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+        const uint32_t ab = lt & 1;
+        mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + ab * acc_stride;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % kPStages, ph = (it / kPStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+          const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sa + a_bytes);
+#pragma unroll
+          for (int k = 0; k < kGK / 16; ++k)
+            umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..9: TMEM lane quarter q = warp % 4 (rows q*32 .. q*32+31), column half hcol
+    const int q = warp & 3;
+    const int hcol = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;               // 0..255 within the epilogue group
+    constexpr int kET = 32 * kPEpiWarps;
+    const int row_bytes = block_n * (int)sizeof(TOut) + 16;
+    constexpr int EV = 16 / sizeof(TOut);
+    const int vpr = block_n / EV;
+    const int drr = kET / vpr, dvv = kET % vpr;
+    // this warp's 16-column chunks: [c_lo, c_hi) in units of 16 columns
+    const int nch = block_n / 16;
+    const int c_lo = hcol == 0 ? 0 : (nch + 1) / 2, c_hi = hcol == 0 ? (nch + 1) / 2 : nch;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const int m0 = (t / ntn) * kGM, n0 = (t % ntn) * block_n;
+      const uint32_t ab = lt & 1;
+      mbar_wait(&acc_full[ab], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + ab * acc_stride + ((uint32_t)(q * 32) << 16);
+      unsigned char* my_row = tile + (size_t)row * row_bytes;
+      // all TMEM loads of this warp's columns are issued before the single wait (<= 6 chunks of 16 columns)
+      uint32_t r[6][16];
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (c_lo + j < c_hi) tmem_ld16(trow + (uint32_t)((c_lo + j) * 16), r[j]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // the accumulator can go back to the MMA warp as soon as every epilogue warp has its registers
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (c_lo + j < c_hi)
+          stage16<TOut>(reinterpret_cast<TOut*>(my_row) + (c_lo + j) * 16, r[j], bias, n0 + (c_lo + j) * 16, N);
+      asm volatile("bar.sync 1, %0;" ::"n"(kET) : "memory");   // staged tile complete (epilogue warps only)
+      int rr = et / vpr, vv = et % vpr;
+      const int total = kGM * vpr;
+#pragma unroll 4
+      for (int idx = et; idx < total; idx += kET) {
+        const int m = m0 + rr, n = n0 + vv * EV;
+        if (m < M && n < N) {
+          uint4 val = *reinterpret_cast<const uint4*>(tile + (size_t)rr * row_bytes + (size_t)vv * 16);
+          TOut* dst = C + (int64_t)m * ldc + n;
+          if (addend != nullptr) {
+            const uint4 ad = *reinterpret_cast<const uint4*>(addend + (int64_t)m * ldc + n);
+            TOut* pv = reinterpret_cast<TOut*>(&val);
+            const TOut* pa = reinterpret_cast<const TOut*>(&ad);
+#pragma unroll
+            for (int j = 0; j < EV; ++j) pv[j] = from_f<TOut>(to_f(pv[j]) + to_f(pa[j]));
+          }
+          *reinterpret_cast<uint4*>(dst) = val;
+        }
+        rr += drr;
+        vv += dvv;
+        if (vv >= vpr) {
+          vv -= vpr;
+          ++rr;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kET) : "memory");   // tile may be overwritten by the next tile's staging
+    }
+  }
+  __syncwarp();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -338,6 +497,20 @@ extern "C" int bimamba_gemm_nt_block_n_k(int N, int K) {
 }
 extern "C" int bimamba_gemm_nt_block_n(int N) { return bimamba_gemm_nt_block_n_k(N, 0); }
 
+// Tile width of the persistent variant: these products are bound by L2 traffic (A is re-read once per N tile, B
+// once per M tile), so it takes the widest tile (<= 192 columns: two accumulators fit the 512 TMEM columns) that
+// splits N evenly.
+static int persist_block_n(int N) {
+  int best = 0;
+  long best_cost = 1L << 60;
+  for (int bn = 192; bn >= 16; bn -= 16) {
+    const int tiles = (N + bn - 1) / bn;
+    const long cost = ((long)tiles * bn - N) * 8 + tiles * 64;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                                const float* bias, const void* addend, int64_t M, int N, int K, int in_dtype,
                                int out_dtype, bimamba_stream_t stream) {
@@ -353,6 +526,19 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
   if (M > (int64_t)kGM * 2147483647LL / 2) { set_err("gemm: M too large"); return -3; }
   int block_n = bimamba_gemm_nt_block_n_k(N, K);
   int max_stages = kGStagesMax;
+  // persistent warp-specialised variant when there is more than one tile per SM (and rows are 16-byte friendly)
+  const char* kv = getenv("BIMAMBA_GEMM_KERNEL");   // tuning experiments only: "tile" | "persist"
+  const int osz = out_dtype == BIMAMBA_F32 ? 4 : 2;
+  const bool can_stage = (N % (16 / osz) == 0) && (ldc % (16 / osz) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                         (!addend || (reinterpret_cast<uintptr_t>(addend) & 15) == 0);
+  bool persist = false;
+  {
+    const int bnp = persist_block_n(N);
+    const int64_t nt = ((M + kGM - 1) / kGM) * ((N + bnp - 1) / bnp);
+    persist = can_stage && nt >= 4 * 148;   // measured: below ~4 tiles per SM the one-tile-per-CTA kernel wins
+    if (kv) persist = can_stage && kv[0] == 'p';
+    if (persist) block_n = bnp;
+  }
   if (const char* ov = getenv("BIMAMBA_GEMM_BN")) block_n = atoi(ov);        // tuning experiments only
   if (const char* ov = getenv("BIMAMBA_GEMM_STAGES")) max_stages = atoi(ov);  // tuning experiments only
   CUtensorMap map_a, map_b;
@@ -377,6 +563,32 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kGM >> 4) << 24);
   dim3 grid((unsigned)((M + kGM - 1) / kGM), (unsigned)((N + block_n - 1) / block_n));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t ntiles = (int64_t)grid.x * grid.y;
+  if (persist && staged) {
+    const uint32_t acc_stride = (uint32_t)((block_n + 31) / 32 * 32);
+    uint32_t pcols = 32;
+    while (pcols < 2 * acc_stride) pcols <<= 1;
+    const size_t psmem = (size_t)kPStages * stage_bytes + tile_bytes + 1024;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const unsigned pgrid = (unsigned)(ntiles < sms ? ntiles : sms);
+#define GEMM_PLAUNCH(TOUT)                                                                                         \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(gemm_nt_persist_kernel<TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);   \
+    gemm_nt_persist_kernel<TOUT><<<pgrid, kPThreads, psmem, st>>>(map_a, map_b, reinterpret_cast<TOUT*>(C), bias,   \
+                                                                  reinterpret_cast<const TOUT*>(addend), (int)M, N, K, \
+                                                                  ldc, block_n, idesc, pcols, acc_stride);         \
+  } while (0)
+    if (psmem <= 220 * 1024) {
+      if (out_dtype == BIMAMBA_F32) GEMM_PLAUNCH(float);
+      else if (out_dtype == BIMAMBA_BF16) GEMM_PLAUNCH(__nv_bfloat16);
+      else GEMM_PLAUNCH(__half);
+#undef GEMM_PLAUNCH
+      cudaError_t pe = cudaGetLastError();
+      if (pe != cudaSuccess) { set_err(cudaGetErrorString(pe)); return (int)pe; }
+      return 0;
+    }
+  }
 #define GEMM_LAUNCH(TOUT)                                                                                          \
   do {                                                                                                             \
     cudaFuncSetAttribute(gemm_nt_kernel<TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \

@@ -257,3 +257,18 @@ def test_scan_forward_variants(lanes, dtype, monkeypatch):
     for L, D in ((201, 288), (37, 40), (499, 17)):
         errs = _run_both(2, D, L, dtype, seed=L + D)
         assert max(errs.values()) < TOL[dtype], (lanes, L, D, errs)
+
+
+@pytest.mark.parametrize("kernel", ["tile", "persist"])
+def test_gemm_nt_kernel_variants(kernel, monkeypatch):
+    """Both tcgen05 kernels (one tile per CTA; persistent warp-specialised with two TMEM accumulators) forced in
+    turn, incl. the 192-column tiles and a tile list several times the SM count."""
+    monkeypatch.setenv("BIMAMBA_GEMM_KERNEL", kernel)
+    for M, N, K in ((12864, 576, 144), (40000, 288, 48), (300, 144, 576), (70000, 48, 288)):
+        g = torch.Generator().manual_seed(M + N)
+        A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+        B = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+        bias = torch.randn(N, generator=g).cuda()
+        out = bm.ops.gemm_nt(A, B, bias=bias, out_dtype=torch.float32)
+        ref = A.double() @ B.double().t() + bias.double()
+        assert rel(out, ref) < 1e-5, (kernel, M, N, K)
