@@ -365,12 +365,17 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: pinned host input -> H2D -> step -> loss.item() every step ----
+    pipelined = use_graph and world == 1
     for _ in range(2):
-        float(step(x_host))
+        float(step(x_host).detach())
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        loss_val = float(step(x_host))            # .item(): D2H read + host sync, like src/main.py:1123
+    if pipelined:      # public API: the H2D copy of batch i+1 overlaps step i; every step's loss is read back
+        for loss_val in runner.run_pipelined(x_host for _ in range(K)):
+            pass
+    else:
+        for _ in range(K):
+            loss_val = float(step(x_host).detach())   # .item(): D2H read + host sync, like src/main.py:1123
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
 
@@ -409,9 +414,9 @@ def run_ours(args, rank, world, local_rank):
             "peak_source": peak_src, "avg_launch_ms": bwd_ms,
             "algorithmic_bytes_per_launch": alg,
             "note": "bf16 IO, (7D+4N)*2 B per frame per direction (SURVEY 8d) x 12864 frames x 2 directions.  The kernel is "
-                    "bound by instruction issue, not by HBM (DESIGN.md 4.2: ~490 SASS instructions per element at 37 %% issue "
-                    "utilisation; the config-2 working set also sits in the 126 MB L2), so the HBM fraction is low by "
-                    "construction.  scan_fwd (MUFU-bound, DESIGN.md 4.1) avg launch %.4f ms = %.1f GB/s algorithmic"
+                    "bound by instruction issue and the shared-memory pipe, not by HBM (DESIGN.md 4.2: ncu issue-active 58 %%, "
+                    "L1TEX data pipe 66 %%, DRAM 5 %%; the config-2 working set also sits in the 126 MB L2), so the HBM "
+                    "fraction is low by construction.  scan_fwd (MUFU-bound, DESIGN.md 4.1) avg launch %.4f ms = %.1f GB/s algorithmic"
                     % (fwd_ms, scan_bytes(B * L, 2, 2, False) / (fwd_ms * 1e-3) / 1e9),
             "kernels_ms": {k: round(statistics.mean(v[len(v) // 3:]), 4) for k, v in times.items()},
         }
@@ -429,7 +434,8 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K,
-                    "api": "bimamba_b200.GraphedTrainStep.run(pinned_host_x) -> loss.item()" if use_graph
+                    "api": ("bimamba_b200.GraphedTrainStep.run_pipelined(pinned host batches) -> float(loss) per step" if pipelined else
+                            "bimamba_b200.GraphedTrainStep.run(pinned_host_x) -> loss.item()") if use_graph
                            else "BiMambaBackend.forward_features + backward, eager"},
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,

@@ -48,6 +48,41 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.static_loss
 
+    def run_pipelined(self, host_batches):
+        """Generator over pinned host batches: yields float(loss) of every step (a device->host read per step, like
+        src/main.py:1123).  The host->device copy of batch i+1 runs on a copy stream while step i replays (double
+        buffered staging + one device-to-device copy into the graph's static input), which is what a data loader
+        with pinned memory does for the reference loop."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = [torch.empty_like(self.static_x) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._consumed = [torch.cuda.Event() for _ in range(2)]
+        copy, main = self._copy_stream, torch.cuda.current_stream()
+        it = iter(host_batches)
+        nxt = next(it, None)
+        if nxt is not None:
+            copy.wait_stream(main)
+            with torch.cuda.stream(copy):
+                self._stage[0].copy_(nxt, non_blocking=True)
+                self._ready[0].record(copy)
+        idx = 0
+        while nxt is not None:
+            cur = idx & 1
+            main.wait_event(self._ready[cur])
+            self.static_x.copy_(self._stage[cur], non_blocking=True)
+            self._consumed[cur].record(main)
+            nxt = next(it, None)
+            if nxt is not None:
+                with torch.cuda.stream(copy):
+                    if idx > 0:
+                        copy.wait_event(self._consumed[1 - cur])
+                    self._stage[1 - cur].copy_(nxt, non_blocking=True)
+                    self._ready[1 - cur].record(copy)
+            self.graph.replay()
+            yield float(self.static_loss.detach())
+            idx += 1
+
 
 class GraphedForward:
     """Captures a no-grad forward (scoring, src/main.py:958-995) for a fixed input shape."""

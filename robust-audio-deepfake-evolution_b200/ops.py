@@ -609,18 +609,9 @@ def cast_transpose(W: torch.Tensor, dtype):
     return dst, dstT
 
 
-def pack_x_proj(W_x: torch.Tensor, R: int, N: int, dtype) -> torch.Tensor:
-    """x_proj.weight (R + 2N, D) -> (48, D): rows [B | C | dt_r | 0] so one GEMM emits the row layout the
-    scan kernels stage with aligned vector copies (mamba_block.py:73-75 splits [dt_r | B | C])."""
-    D = W_x.shape[1]
-    Wp = torch.zeros((XW, D), device=W_x.device, dtype=dtype)
-    Wp[:N] = W_x[R:R + N]
-    Wp[N:2 * N] = W_x[R + N:R + 2 * N]
-    Wp[2 * N:2 * N + R] = W_x[:R]
-    return Wp
-
-
 def unpack_x_proj_grad(dWp: torch.Tensor, R: int, N: int) -> torch.Tensor:
+    """Gradient of the repacked (48, D) x_proj weight [B | C | dt_r | 0] -> x_proj.weight's own row order
+    [dt_r | B | C] (mamba_block.py:73-75)."""
     return torch.cat([dWp[2 * N:2 * N + R], dWp[:N], dWp[N:2 * N]], dim=0)
 
 
