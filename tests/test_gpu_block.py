@@ -198,3 +198,33 @@ def test_graphed_train_step_pipelined_matches_sequential():
     assert len(pip) == len(seq)
     for u, v in zip(seq, pip):
         assert abs(u - v) <= 2e-3 * max(1.0, abs(u)), (seq, pip)
+
+
+@pytest.mark.parametrize("d_model,Bsz,L", [(64, 3, 77), (80, 2, 130), (256, 2, 40)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_block_other_widths(d_model, Bsz, L, dtype):
+    """The block is not specialised to d_model 144: other widths (d_inner 128 / 160 / 512, dt_rank 4 / 5 / 16, channel
+    counts that do not fill the kernels' 32-channel groups) against the oracle, outputs and every gradient."""
+    p64 = orc.init_mamba_params(d_model, 16, seed=d_model, dtype=torch.float64)
+    m = bm.Mamba(d_model, 16).cuda()
+    _load_mamba(m, {k: v.numpy() for k, v in p64.items()})
+    g = torch.Generator().manual_seed(d_model + L)
+    x = torch.randn(Bsz, L, d_model, generator=g)
+    cot = torch.randn(Bsz, L, d_model, generator=g)
+    pr = {k: v.float().double().requires_grad_(True) for k, v in p64.items()}
+    xr = x.double().requires_grad_(True)
+    ref = orc.bimamba_ref(pr, xr)
+    (ref * cot.double()).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    if dtype == torch.float32:
+        out = m.forward_bidirectional(xd)
+        tol = 1e-4
+    else:
+        with torch.autocast("cuda", dtype=dtype):
+            out = m.forward_bidirectional(xd)
+        tol = 2e-2
+    out.float().backward(cot.cuda())
+    assert rel(out, ref) < tol
+    assert rel(xd.grad, xr.grad) < tol
+    for name, prm in m.named_parameters():
+        assert rel(prm.grad, pr[name].grad) < tol, name
