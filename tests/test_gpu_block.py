@@ -228,3 +228,26 @@ def test_block_other_widths(d_model, Bsz, L, dtype):
     assert rel(xd.grad, xr.grad) < tol
     for name, prm in m.named_parameters():
         assert rel(prm.grad, pr[name].grad) < tol, name
+
+
+def test_backward_is_bitwise_deterministic():
+    """No atomics anywhere on the path: two runs of the encoder layer's forward + backward at the benchmark shape give
+    bit-identical outputs and gradients (also a race detector for the hand-synchronised shared-memory phases)."""
+    torch.manual_seed(5)
+    enc = bm.PN_BiMambas_Encoder(144, 16).cuda()
+    with torch.no_grad():
+        enc.mamba.A_log.add_(0.1 * torch.randn_like(enc.mamba.A_log))
+    x = torch.randn(64, 201, 144, device="cuda")
+    runs = []
+    for _ in range(3):
+        for p in enc.parameters():
+            p.grad = None
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = enc(xi)
+        out.float().square().mean().backward()
+        torch.cuda.synchronize()
+        runs.append([out.detach().clone(), xi.grad.clone()] + [p.grad.clone() for p in enc.parameters()])
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert torch.equal(a, b)
