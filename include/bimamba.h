@@ -155,6 +155,15 @@ int bimamba_reduce_partials(const float* part, void* out, int64_t groups, int64_
                             int64_t part_gs, int64_t row_stride, int64_t out_gs,
                             int out_dtype, int accumulate, bimamba_stream_t stream);
 
+/* Weight-gradient product C[N1, N2] = A[M, N1]^T . B[M, N2] (bf16 / fp16 row-major activations, contraction over
+ * the B*L rows; C fp32 row-major) on the tcgen05 tensor cores with MN-major operands: dW = dY^T X of the nn.Linear
+ * layers (autograd of mamba_block.py:48, :73, :62 and DualStreamSEMamba.py:460-464).  The contraction is split over
+ * nsplit = bimamba_gemm_tn_splits(M, N1, N2) CTAs (one wave); `part` is a caller-allocated workspace of
+ * nsplit * N1 * N2 floats; the splits are summed in fixed order (deterministic) by a second kernel of the same call. */
+int bimamba_gemm_tn_splits(int64_t M, int N1, int N2);
+int bimamba_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, float* part, int64_t M, int N1,
+                    int N2, int in_dtype, bimamba_stream_t stream);
+
 /* Column sums of a (rows, cols) matrix with row stride ld (elements): the bias gradients of the Linear layers.
  * Writes fp32 partials part (nslices, cols), nslices = bimamba_colsum_slices(rows); finish with
  * bimamba_reduce_partials. */

@@ -439,6 +439,129 @@ gemm_nt_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   }
 }
 
+// ---- weight-gradient product: C[N1, N2] = A[M, N1]^T . B[M, N2]  (contraction over the rows) ------------------
+// Both operands are read as they lie in memory (row-major activations), i.e. as MN-major UMMA operands: TMA loads
+// 64-feature x 64-row boxes with the 128-byte swizzle; a 64 x 8 sub-block is one 1024-byte swizzle atom, atoms of
+// the same 64 features follow each other along the contraction (SBO = 1024 B), 64-feature groups are 8 KB apart
+// (LBO).  One operand ("P") takes the 128 TMEM lanes of the tile, the other ("Q") its columns.  The long contraction
+// (M = B*L*ndir rows) is split over blockIdx.z so that the grid is one wave; every CTA writes an fp32 partial tile
+// part[z][q][p] (lanes run along p: 128-byte coalesced stores) and tn_reduce_kernel sums the splits in fixed order
+// (deterministic, unlike an atomic split-K), transposing on the way out when P is the row index of C.
+constexpr int kTNStages = 3;
+constexpr int kTNBox = 64 * 64 * 2;   // bytes of one 64-feature x 64-row box
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(kTNBox >> 4) << 16;   // LBO: next 64-feature group
+  d |= (uint64_t)(1024 >> 4) << 32;     // SBO: next 8 rows of the contraction
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(kGThreads)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
+               float* __restrict__ part, int M, int NP, int NQ, int block_q, int kb_per_split, uint32_t idesc,
+               uint32_t tmem_cols) {
+  extern __shared__ __align__(1024) unsigned char gsm[];
+  __shared__ __align__(8) uint64_t full_bar[kTNStages], empty_bar[kTNStages], accum_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = blockIdx.x * kGM, q0 = blockIdx.y * block_q;
+  const int nkb_all = (M + 63) / 64;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int nkb = min(kb_per_split, nkb_all - kb0);
+  const int nbq = (block_q + 63) / 64;
+  const uint32_t p_bytes = 2 * kTNBox, q_bytes = (uint32_t)nbq * kTNBox;
+  const uint32_t stage_bytes = p_bytes + q_bytes;
+  unsigned char* base = gsm + ((1024u - (smem_u32(gsm) & 1023u)) & 1023u);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTNStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % kTNStages;
+      if (i >= kTNStages) mbar_wait(&empty_bar[s], ((i / kTNStages) - 1) & 1);
+      unsigned char* sp = base + (size_t)s * stage_bytes;
+      const int m0 = (kb0 + i) * 64;
+      mbar_expect_tx(&full_bar[s], p_bytes + q_bytes);
+      tma_load_2d(sp, &map_p, &full_bar[s], p0, m0);
+      tma_load_2d(sp + kTNBox, &map_p, &full_bar[s], p0 + 64, m0);
+      for (int gb = 0; gb < nbq; ++gb) tma_load_2d(sp + p_bytes + gb * kTNBox, &map_q, &full_bar[s], q0 + 64 * gb, m0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % kTNStages;
+      mbar_wait(&full_bar[s], (i / kTNStages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sp = smem_u32(base + (size_t)s * stage_bytes);
+      const uint64_t dp = make_mnmajor_sw128_desc(sp), dq = make_mnmajor_sw128_desc(sp + p_bytes);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)   // 16 rows of the contraction per instruction = two 8-row atoms = 2048 bytes
+        umma_f16(tmem_base, dp + (uint64_t)(k * (2048 >> 4)), dq + (uint64_t)(k * (2048 >> 4)), idesc, (i | k) != 0 ? 1u : 0u);
+      umma_commit(&empty_bar[s]);
+    }
+    umma_commit(&accum_bar);
+  }
+  __syncwarp();
+  if (nkb > 0) {
+    mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  __syncwarp();
+  const int pi = p0 + warp * 32 + lane;      // this thread's P feature (TMEM lane)
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  float* dst = part + ((int64_t)blockIdx.z * NQ + q0) * NP + pi;
+  for (int c = 0; c < block_q; c += 16) {
+    uint32_t r[16];
+    if (nkb > 0) {
+      tmem_ld16(trow + (uint32_t)c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = 0u;
+    }
+    if (pi < NP) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (q0 + c + j < NQ) dst[(int64_t)(c + j) * NP] = __uint_as_float(r[j]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// out = sum over the splits of part[z][q][p], in split order; p_is_row: out is (NP, NQ) row-major, else (NQ, NP).
+__global__ void __launch_bounds__(256)
+tn_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nsplit, int NP, int NQ, int p_is_row) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int total = NP * NQ;
+  if (idx >= total) return;
+  float acc = 0.f;
+  for (int z = 0; z < nsplit; ++z) acc += part[(int64_t)z * total + idx];
+  const int q = idx / NP, p = idx - q * NP;
+  out[p_is_row ? (int64_t)p * NQ + q : (int64_t)idx] = acc;
+}
+
 // ---- host side -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -455,12 +578,13 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    int box_cols = kGK) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_err("cuTensorMapEncodeTiled is not available from the driver"); return -20; }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kGK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = dtype == BIMAMBA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -600,6 +724,76 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
   else if (out_dtype == BIMAMBA_BF16) GEMM_LAUNCH(__nv_bfloat16);
   else GEMM_LAUNCH(__half);
 #undef GEMM_LAUNCH
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+namespace {
+struct TnPlan { int p_is_a, NP, NQ, block_q, nsplit, per; };
+inline int64_t tn_padded(int np, int nq, int* bq_out) {
+  const int nblk = (nq + 255) / 256;
+  const int bq = ((nq + nblk - 1) / nblk + 15) / 16 * 16;
+  if (bq_out) *bq_out = bq;
+  return (int64_t)((np + kGM - 1) / kGM) * kGM * ((nq + bq - 1) / bq) * bq;
+}
+inline TnPlan tn_plan(int64_t M, int N1, int N2) {
+  TnPlan pl;
+  int bq_a, bq_b;
+  const int64_t cost_a = tn_padded(N1, N2, &bq_a);   // A's features on the TMEM lanes
+  const int64_t cost_b = tn_padded(N2, N1, &bq_b);
+  pl.p_is_a = cost_a < cost_b;                        // tie: B on the lanes, no transpose on the way out
+  pl.NP = pl.p_is_a ? N1 : N2;
+  pl.NQ = pl.p_is_a ? N2 : N1;
+  pl.block_q = pl.p_is_a ? bq_a : bq_b;
+  const int64_t tiles = (int64_t)((pl.NP + kGM - 1) / kGM) * ((pl.NQ + pl.block_q - 1) / pl.block_q);
+  const int64_t nkb = (M + 63) / 64;
+  int64_t want = 148 / tiles;                         // one wave, one CTA per SM
+  if (want > nkb) want = nkb;
+  if (want < 1) want = 1;
+  pl.per = (int)((nkb + want - 1) / want);
+  pl.nsplit = (int)((nkb + pl.per - 1) / pl.per);
+  return pl;
+}
+}  // namespace
+
+extern "C" int bimamba_gemm_tn_splits(int64_t M, int N1, int N2) {
+  if (M <= 0 || N1 <= 0 || N2 <= 0) return 1;
+  return tn_plan(M, N1, N2).nsplit;
+}
+
+extern "C" int bimamba_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, float* part, int64_t M,
+                               int N1, int N2, int in_dtype, bimamba_stream_t stream) {
+  if (M == 0 || N1 == 0 || N2 == 0) return 0;
+  if (!A || !B || !C || !part) { set_err("gemm_tn: null operand"); return -1; }
+  if (M < 0 || N1 < 0 || N2 < 0) { set_err("gemm_tn: bad sizes"); return -3; }
+  if (in_dtype != BIMAMBA_BF16 && in_dtype != BIMAMBA_F16) { set_err("gemm_tn: operands must be bf16 or fp16"); return -6; }
+  if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) {
+    set_err("gemm_tn: operands must be 16-byte aligned with row strides that are multiples of 8 elements");
+    return -7;
+  }
+  const TnPlan pl = tn_plan(M, N1, N2);
+  CUtensorMap map_p, map_q;
+  int rc = make_map(&map_p, pl.p_is_a ? A : B, in_dtype, M, pl.NP, pl.p_is_a ? lda : ldb, 64, 64);
+  if (rc) return rc;
+  rc = make_map(&map_q, pl.p_is_a ? B : A, in_dtype, M, pl.NQ, pl.p_is_a ? ldb : lda, 64, 64);
+  if (rc) return rc;
+  const int nbq = (pl.block_q + 63) / 64;
+  const size_t smem = (size_t)kTNStages * (2 + nbq) * kTNBox + 1024;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < pl.block_q) tmem_cols <<= 1;
+  const uint32_t fmt = in_dtype == BIMAMBA_BF16 ? 1u : 0u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
+                         ((uint32_t)(pl.block_q >> 3) << 17) | ((uint32_t)(kGM >> 4) << 24);
+  dim3 grid((unsigned)((pl.NP + kGM - 1) / kGM), (unsigned)((pl.NQ + pl.block_q - 1) / pl.block_q), (unsigned)pl.nsplit);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 6 * kTNBox + 1024);
+    attr_set = true;
+  }
+  gemm_tn_kernel<<<grid, kGThreads, smem, st>>>(map_p, map_q, part, (int)M, pl.NP, pl.NQ, pl.block_q, pl.per, idesc, tmem_cols);
+  tn_reduce_kernel<<<(unsigned)(((int64_t)N1 * N2 + 255) / 256), 256, 0, st>>>(part, C, pl.nsplit, pl.NP, pl.NQ, pl.p_is_a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

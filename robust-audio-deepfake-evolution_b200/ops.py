@@ -425,6 +425,29 @@ def gemm_nt(A, B, bias=None, addend=None, out_dtype=None):
     return out
 
 
+def gemm_tn(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """A (M, N1)^T . B (M, N2) -> (N1, N2) fp32: the weight gradient dY^T X on the tcgen05 kernel (MN-major operands,
+    deterministic split over the M rows).  fp32 / misaligned operands use the library product."""
+    if not (_tc_ok(A, B) and os.environ.get("BIMAMBA_WGRAD", "tcgen05") != "cublas"):
+        return mm_f32(A.t(), B)
+    lib = _lib.load()
+    M, N1 = A.shape
+    N2 = B.shape[1]
+    ns = lib.bimamba_gemm_tn_splits(M, N1, N2)
+    part = torch.empty((ns, N1 * N2), device=A.device, dtype=torch.float32)
+    out = torch.empty((N1, N2), device=A.device, dtype=torch.float32)
+    with _timed("gemm_tn"):
+        _lib.check(lib.bimamba_gemm_tn(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), _ptr(part), M, N1, N2,
+                                       _dt(A), _stream()), "bimamba_gemm_tn")
+    _lib.launch_count += 1   # two kernels per call
+    return out
+
+
+def wgrad(dY: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """dY (M, N_out)^T . X (M, N_in) -> (N_out, N_in) fp32: the weight gradient of y = x W^T."""
+    return gemm_tn(dY, X)
+
+
 def mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a @ b with an fp32 result: the weight-gradient products (contraction over B*L) accumulate and leave in fp32
     (library GEMM; 16-bit operands, no separate cast of the result)."""
@@ -489,13 +512,13 @@ class FeedForwardFn(torch.autograd.Function):
                 g = g.contiguous()
             with _Fork() as f2:                       # second Linear's parameter gradients || its data gradient
                 db2 = colsum(g)
-                dW2 = mm_f32(g.t(), a)
+                dW2 = wgrad(g, a)
             da = gemm_nt(g, W2T)
             dh = torch.ops.aten.gelu_backward(da, h)
             f2.join()
             with _Fork() as f1:                       # first Linear's parameter gradients || its data gradient
                 db1 = colsum(dh)
-                dW1 = mm_f32(dh.t(), x2)
+                dW1 = wgrad(dh, x2)
             dx = gemm_nt(dh, W1T)
             f1.join()
         return (dx.view(shape).to(xdt), dW1.to(w1dt), db1.to(b1dt), dW2.to(w2dt), db2.to(b2dt),
@@ -688,7 +711,7 @@ class BiMambaInnerFn(torch.autograd.Function):
             # out_proj
             y2 = rows2d(y).view(M, ndir * D)
             with _Fork() as f_out:                                            # out_proj weight gradient || dy, scan
-                dW_out2 = mm_f32(g2.t(), y2)                                # (dm, ndir*D)
+                dW_out2 = wgrad(g2, y2)                                    # (dm, ndir*D)
                 dW_out = dW_out2[:, :D] + dW_out2[:, D:] if ndir > 1 else dW_out2
             dy = gemm_nt(g2, WoT)                                             # (M, D), shared by both directions
             # scan (both directions in one launch); dy and z are broadcast over the direction axis
@@ -701,9 +724,8 @@ class BiMambaInnerFn(torch.autograd.Function):
             dxdbl = torch.cat([rows2d(dbc), gemm_nt(dd2, WdT)], dim=1)        # (M*ndir, 48) [dB | dC | ddt_r | 0]
             xc2 = rows2d(xc)
             with _Fork() as f_w:                                              # dt_proj / x_proj weight gradients || dxc, conv
-                dW_dt = mm_f32(dd2.t(), xdbl)[:, 2 * N:2 * N + R]           # (D, R); full-row GEMM: a 9-column strided
-                                                                              # operand would fall off cuBLAS's fast kernels
-                dW_xp = mm_f32(dxdbl.t(), xc2)                              # (48, D)
+                dW_dt = wgrad(dd2, xdbl)[:, 2 * N:2 * N + R]               # (D, R) of the full-row product
+                dW_xp = wgrad(dxdbl, xc2)                                   # (48, D)
             # x_proj
             dxc = gemm_nt(dxdbl, WxpT, addend=rows2d(du))                     # (M*ndir, D)
             dxc4 = dxc.view(Bsz, L, ndir, D).permute(0, 2, 1, 3)
@@ -714,7 +736,7 @@ class BiMambaInnerFn(torch.autograd.Function):
             K = cw32.shape[1]
             # in_proj
             with _Fork() as f_in:                                             # in_proj weight gradient || its data gradient
-                dW_in = mm_f32(dxz.t(), x2)                                 # (2D, dm)
+                dW_in = wgrad(dxz, x2)                                      # (2D, dm)
             dx = gemm_nt(dxz, WiT).view(Bsz, L, dm)
             dA_log = dA * A32                                                 # A = -exp(A_log)
             f_out.join()

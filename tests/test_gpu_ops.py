@@ -272,3 +272,18 @@ def test_gemm_nt_kernel_variants(kernel, monkeypatch):
         out = bm.ops.gemm_nt(A, B, bias=bias, out_dtype=torch.float32)
         ref = A.double() @ B.double().t() + bias.double()
         assert rel(out, ref) < 1e-5, (kernel, M, N, K)
+
+
+@pytest.mark.parametrize("M,N1,N2", [(12864, 576, 144), (25728, 288, 48), (12864, 576, 144), (130, 128, 16), (1000, 144, 576),
+                                     (64, 64, 64), (201, 200, 41 + 7)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gemm_tn_weight_gradient(M, N1, N2, dtype):
+    """dW = dY^T X (contraction over the B*L rows, MN-major tcgen05 operands, deterministic split) vs fp64."""
+    g = torch.Generator().manual_seed(M + N1 + N2)
+    A = torch.randn(M, N1, generator=g).to(dtype).cuda()
+    B = torch.randn(M, N2, generator=g).to(dtype).cuda()
+    out = bm.ops.gemm_tn(A, B)
+    assert out.dtype == torch.float32 and out.shape == (N1, N2)
+    ref = A.double().t() @ B.double()
+    assert rel(out, ref) < 1e-5
+    assert torch.equal(out, bm.ops.gemm_tn(A, B))
