@@ -85,7 +85,7 @@ def oracle_step_fn(batch, frames):
         for p in layers:
             for v in p.values():
                 v.grad = None
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
@@ -162,9 +162,16 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def ready(self, timeout=5.0):
+        """Block until nvidia-smi has delivered its first sample (its start-up takes longer than a short timed run)."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
+    def stop(self, windows):
+        """Median SM clock / throttle reasons over the samples that fall inside the timed windows [(t0, t1), ...]."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -172,8 +179,9 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        inside = [ln for t, ln in self.lines if any(a <= t <= b for a, b in windows)]
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -344,25 +352,28 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
-
-    # ---- device-resident timing: per-step CUDA events, L2 flushed (untimed) between steps ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    if rank == 0:
+        sampler.ready()
+    barrier()
+
+    # ---- device-resident timing: per-step CUDA events, L2 flushed (untimed) between steps ----
     K = args.steps
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
+    w0 = time.perf_counter()
     for s, e in evs:
         flush.zero_()
         s.record()
         step()
         e.record()
     barrier()
+    w1 = time.perf_counter()
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: pinned host input -> H2D -> step -> loss.item() every step ----
     pipelined = use_graph and world == 1
@@ -377,7 +388,9 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(K):
             loss_val = float(step(x_host).detach())   # .item(): D2H read + host sync, like src/main.py:1123
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t1 = time.perf_counter()
+    e2e_ms = (t1 - t0) * 1e3
+    clocks = sampler.stop([(w0, w1), (t0, t1)]) if rank == 0 else None   # both timed regions
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)

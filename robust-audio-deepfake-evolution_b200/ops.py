@@ -151,10 +151,11 @@ def conv_fwd_raw(x, weight, bias, out, silu: bool):
         _lib.check(rc, "bimamba_causal_conv1d_fwd")
 
 
-def conv_bwd_raw(x, weight, bias, dout, dx, silu: bool, dz_in=None, dz_out=None):
+def conv_bwd_raw(x, weight, bias, dout, dx, silu: bool, dz_in=None, dz_out=None, defer: Optional[list] = None):
     """dout (B, ndir, L, D) view; dx (B, L, D) (may be a strided view).  Optionally folds the sum of the
     per-direction gate gradients dz_in (same strides as dout) into dz_out (same strides as dx).
-    Returns dwb (D, K+1) fp32 [dw | dbias]."""
+    Returns dwb (D, K+1) fp32 [dw | dbias]; with `defer` (a list) its fixed-order sum over the CTAs' partials runs on
+    the side stream and the fork is appended to the list (join() before using dwb)."""
     lib = _lib.load()
     Bsz, L, D = x.shape
     ndir = dout.shape[1]
@@ -176,7 +177,13 @@ def conv_bwd_raw(x, weight, bias, dout, dx, silu: bool, dz_in=None, dz_out=None)
     dwb = torch.empty((D, K + 1), device=x.device, dtype=torch.float32)
     if Bsz * L == 0:
         return dwb.zero_()
-    reduce_raw(part, dwb, groups=1, rows=nsl, cols=D * (K + 1), part_gs=0, row_stride=D * (K + 1), out_gs=0)
+    if defer is None:
+        reduce_raw(part, dwb, groups=1, rows=nsl, cols=D * (K + 1), part_gs=0, row_stride=D * (K + 1), out_gs=0)
+    else:
+        with _Fork() as f:
+            reduce_raw(part, dwb, groups=1, rows=nsl, cols=D * (K + 1), part_gs=0, row_stride=D * (K + 1), out_gs=0)
+        f.keep = (part,)
+        defer.append(f)
     return dwb
 
 
@@ -230,9 +237,11 @@ def scan_fwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, wa
 
 
 def scan_bwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, dout, ckpt, ypre,
-                 dtr_padded: bool = False, bc_out_dtype=None):
+                 dtr_padded: bool = False, bc_out_dtype=None, defer: Optional[list] = None):
     """Returns (du, ddelta, dz, dbc, dA, dD, dbias): du / ddelta / dz are (B, ndir, L, dim) views of
-    (B, L, ndir, dim) storage; dbc is (B, ndir, L, 32) = [dB | dC] likewise; dA (dim, N), dD, dbias (dim)."""
+    (B, L, ndir, dim) storage; dbc is (B, ndir, L, 32) = [dB | dC] likewise; dA (dim, N), dD, dbias (dim).
+    With `defer` (a list) the parameter-gradient sums dA / dD / dbias are enqueued on the side stream and the fork is
+    appended to the list: the caller must join() it before using them."""
     lib = _lib.load()
     Bsz, ndir, L, dim = u.shape
     N = A.shape[1]
@@ -265,14 +274,23 @@ def scan_bwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, do
     reduce_raw(dbc_part, dbc, groups=Bsz, rows=ngroups, cols=cols, part_gs=ngroups * cols, row_stride=cols,
                out_gs=cols)
     dA = torch.empty((dim, N), device=dev, dtype=torch.float32)
-    reduce_raw(dA_part, dA, 1, Bsz * ndir, dim * N, 0, dim * N, 0)
-    dD = dbias = None
-    if D is not None:
-        dD = torch.empty((dim,), device=dev, dtype=torch.float32)
-        reduce_raw(dD_part, dD, 1, Bsz * ndir, dim, 0, dim, 0)
-    if delta_bias is not None:
-        dbias = torch.empty((dim,), device=dev, dtype=torch.float32)
-        reduce_raw(db_part, dbias, 1, Bsz * ndir, dim, 0, dim, 0)
+    dD = torch.empty((dim,), device=dev, dtype=torch.float32) if D is not None else None
+    dbias = torch.empty((dim,), device=dev, dtype=torch.float32) if delta_bias is not None else None
+
+    def param_sums():
+        reduce_raw(dA_part, dA, 1, Bsz * ndir, dim * N, 0, dim * N, 0)
+        if D is not None:
+            reduce_raw(dD_part, dD, 1, Bsz * ndir, dim, 0, dim, 0)
+        if delta_bias is not None:
+            reduce_raw(db_part, dbias, 1, Bsz * ndir, dim, 0, dim, 0)
+
+    if defer is None:
+        param_sums()
+    else:                                  # off the data-gradient chain
+        with _Fork() as f:
+            param_sums()
+        f.keep = (dA_part, dD_part, db_part)
+        defer.append(f)
     return du, ddelta, dz, dbc, dA, dD, dbias
 
 
@@ -716,9 +734,10 @@ class BiMambaInnerFn(torch.autograd.Function):
             dy = gemm_nt(g2, WoT)                                             # (M, D), shared by both directions
             # scan (both directions in one launch); dy and z are broadcast over the direction axis
             dyb = dy.view(Bsz, 1, L, D).expand(Bsz, ndir, L, D)
+            forks = []                                                        # dA / dD / dbias sums run beside the chain
             du, ddelta, dz, dbc, dA, dD, dbdt = scan_bwd_raw(
                 xc, z.unsqueeze(1).expand(Bsz, ndir, L, D), None, xd4[..., :2 * N], xd4[..., 2 * N:], Wd32,
-                A32, D32, bdt32, True, dyb, ckpt, ypre, dtr_padded=True)
+                A32, D32, bdt32, True, dyb, ckpt, ypre, dtr_padded=True, defer=forks)
             # dt_proj (weight gradient in fp32; the data gradient joins the x_proj row)
             dd2 = rows2d(ddelta)                                              # (M*ndir, D)
             dxdbl = torch.cat([rows2d(dbc), gemm_nt(dd2, WdT)], dim=1)        # (M*ndir, 48) [dB | dC | ddt_r | 0]
@@ -732,16 +751,15 @@ class BiMambaInnerFn(torch.autograd.Function):
             # conv (writes dx into the x half and dz_fwd + dz_rev into the z half of dxz)
             dxz = torch.empty_like(xz)
             dxz3 = dxz.view(Bsz, L, 2 * D)
-            dwb = conv_bwd_raw(xs, cw32, cb32, dxc4, dxz3[:, :, :D], True, dz_in=dz, dz_out=dxz3[:, :, D:])
+            dwb = conv_bwd_raw(xs, cw32, cb32, dxc4, dxz3[:, :, :D], True, dz_in=dz, dz_out=dxz3[:, :, D:], defer=forks)
             K = cw32.shape[1]
             # in_proj
             with _Fork() as f_in:                                             # in_proj weight gradient || its data gradient
                 dW_in = wgrad(dxz, x2)                                      # (2D, dm)
             dx = gemm_nt(dxz, WiT).view(Bsz, L, dm)
+            for f in (f_out, f_w, f_in, *forks):
+                f.join()
             dA_log = dA * A32                                                 # A = -exp(A_log)
-            f_out.join()
-            f_w.join()
-            f_in.join()
             dW_x = unpack_x_proj_grad(dW_xp, R, N)
         return (dx.to(xdt), dW_in.to(pdt[0]), dwb[:, :K].reshape(cw_shape).to(pdt[1]), dwb[:, K].to(pdt[2]),
                 dW_x.to(pdt[3]), dW_dt.to(pdt[4]), dbdt.to(pdt[5]), dA_log.to(pdt[6]), dD.to(pdt[7]),
