@@ -28,6 +28,8 @@
 //     (warp, channel) lanes in fixed order through shared memory and written as per-group partials;
 //     dA/dD/dbias are per-(batch, dir, channel) partials.  All cross-CTA sums are done in fixed order
 //     by bimamba_reduce_partials: the whole backward is deterministic (no atomics).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bimamba {
@@ -457,6 +459,7 @@ static void launch_bwd(const bimamba_scan_desc* d, cudaStream_t st) {
 }
 
 int check_desc(const bimamba_scan_desc* d, bool bwd);  // api.cu
+void launch_bwd_lane(const bimamba_scan_desc* d, cudaStream_t st);  // scan_bwd1.cu
 
 }  // namespace bimamba
 
@@ -469,10 +472,16 @@ extern "C" int bimamba_selective_scan_bwd(const bimamba_scan_desc* d, bimamba_st
   const int G = d->group_channels;
   if (G < kBC || G > kMaxKP * kBC || (G % kBC)) { set_err("backward group_channels must be 32, 64, 96 or 128 (use bimamba_scan_plan)"); return -5; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (d->io_dtype) {
-    case BIMAMBA_F32: launch_bwd<float>(d, st); break;
-    case BIMAMBA_BF16: launch_bwd<__nv_bfloat16>(d, st); break;
-    default: launch_bwd<__half>(d, st); break;
+  const char* force = getenv("BIMAMBA_BWD_KERNEL");   // "lane" | "pair": tuning experiments and the parity tests of both
+  const bool lane = force ? force[0] == 'l' : true;
+  if (lane) {
+    launch_bwd_lane(d, st);
+  } else {
+    switch (d->io_dtype) {
+      case BIMAMBA_F32: launch_bwd<float>(d, st); break;
+      case BIMAMBA_BF16: launch_bwd<__nv_bfloat16>(d, st); break;
+      default: launch_bwd<__half>(d, st); break;
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }

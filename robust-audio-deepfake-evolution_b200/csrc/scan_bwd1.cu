@@ -1,0 +1,390 @@
+// Selective scan, backward, ONE LANE PER CHANNEL variant (both time directions in one launch).  sm_100a.
+//
+// Same gradients and the same descriptor / outputs as scan_bwd.cu (autograd of
+// src/models/modules/mamba_block.py:80-120, :61):
+//   g = dout * silu(z);  dz = dout * ypre * silu'(z)
+//   dh[t] = g[t] C[t] + a[t+1] dh[t+1]                       (reverse-time recurrence)
+//   ddelta[t] = sum_n dh a h[t-1] A + u sum_n dh B;  du[t] = g D + delta sum_n dh B
+//   dB[t,n] = sum_d dh delta u;  dC[t,n] = sum_d g h;  dA[n] = sum_t dh a h[t-1] delta
+//
+// Mapping.  A thread owns one channel of one (batch, direction) with all 16 states as 8 float2 (FMUL2 / FFMA2), like
+// the forward: the n-sums are thread-local (no shuffles), delta / softplus / SiLU are evaluated once per element by
+// the thread that needs them (no exchange), and dA / dD / dbias accumulate in registers over the whole sequence.
+//   * time is walked in 8-step chunks (the forward's checkpoint interval) from the last to the first.  The chunk is
+//     re-run forward from its checkpoint and the seven intermediate states h[0..6] are KEPT IN REGISTERS (7 x 16):
+//     with every loop unrolled the kernel sits at ~230 registers, i.e. 8 warps per SM - which is all the Phase-6
+//     shapes offer anyway (batch 64 x 2 directions x 288 channels = 7.8 warps per SM) - and needs no (L, D, N)
+//     tensor, no shared-memory history and one third of the instructions of the state-pair kernel.
+//   * the decay a[t] = exp2(delta A) is recomputed in the reverse pass (MUFU is not the limiter here: 36 per element
+//     against ~270 issue slots).
+//   * dB / dC need a sum over channels: per step every lane writes its 32 products to a padded row of shared memory
+//     (8 STS.128, conflict-free), the warp transposes-and-adds them with 8 LDS.128 + packed adds per lane and two
+//     shuffle levels, and lane v ends with column v of the warp's 32-channel sum.  One warp per CTA
+//     (group_channels = 32) needs no block barrier for this and writes the partial row straight to global;
+//     wider CTAs add the warps in fixed order through shared memory.  bimamba_reduce_partials sums the groups:
+//     deterministic, no atomics.
+//   * u, dout, z, ypre tiles [8 x G], the chunk's B|C|dt_r rows and the checkpoint are staged by 16-byte cp.async
+//     into double buffers one chunk ahead.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace bimamba {
+
+constexpr int kLT = BIMAMBA_CKPT;   // steps per chunk == checkpoint interval (8)
+constexpr int kLMaxThreads = 128;
+constexpr int kRedRow = 36;         // floats per channel row of the dB|dC exchange: 32 + 4 pad (conflict-free 16-byte access)
+static_assert(kLT == 8, "history registers are sized for 8-step chunks");
+
+// kMode: 0 = delta given; 1 = fused dt projection with dt_rank <= 12; 2 = dt_rank <= 16.
+template <typename T, int kMode>
+__global__ void __launch_bounds__(kLMaxThreads) scan_bwd_lane_kernel(const bimamba_scan_desc p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool expl = kMode == 0;
+  constexpr int R4 = kMode == 1 ? 3 : 4;
+  constexpr int kV = 16 / sizeof(T);
+  const int G = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = G >> 5;
+  const int b = blockIdx.z, dir = blockIdx.y, g = blockIdx.x, d0 = g * G, d = d0 + tid;
+  const int ngroups = gridDim.x;
+  const bool ok = d < p.dim;
+  const int L = p.seqlen, nsub = (L + kLT - 1) / kLT;
+  const bool gated = p.z != nullptr, need_yp = gated && p.dz != nullptr;
+  const bool softplus = (p.flags & BIMAMBA_FLAG_SOFTPLUS) != 0;
+  const int R = expl ? 0 : p.dt_rank;
+  const int64_t bd = (int64_t)b * p.ndir + dir;
+
+  const T* gu = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_bs + (int64_t)dir * p.u_ds;
+  const T* gz = gated ? reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_bs + (int64_t)dir * p.z_ds : nullptr;
+  const T* gdl = expl ? reinterpret_cast<const T*>(p.delta) + (int64_t)b * p.delta_bs + (int64_t)dir * p.delta_ds : nullptr;
+  const T* gbc = reinterpret_cast<const T*>(p.bc) + (int64_t)b * p.bc_bs + (int64_t)dir * p.bc_ds;
+  const T* gdtr = expl ? nullptr : reinterpret_cast<const T*>(p.dtr) + (int64_t)b * p.dtr_bs + (int64_t)dir * p.dtr_ds;
+  const T* gdo = reinterpret_cast<const T*>(p.dout) + (int64_t)b * p.dout_bs + (int64_t)dir * p.dout_ds;
+  const int64_t obase = (int64_t)b * p.out_bs + (int64_t)dir * p.out_ds;
+  const T* gyp = need_yp ? reinterpret_cast<const T*>(p.ypre) + obase : nullptr;
+  T* gdu = reinterpret_cast<T*>(p.du) + obase;
+  T* gdd = reinterpret_cast<T*>(p.ddelta) + obase;
+  T* gdz = need_yp ? reinterpret_cast<T*>(p.dz) + obase : nullptr;
+  // partial layout (batch, ngroups, L, ndir, 32): reducing over ngroups leaves rows ordered (b, t, dir)
+  const int64_t pb_ts = (int64_t)p.ndir * 2 * kN;
+  float* partB = p.dbc_part + (((int64_t)b * ngroups + g) * L) * pb_ts + dir * 2 * kN;
+  const float* gck = p.ckpt ? p.ckpt + bd * nsub * (int64_t)p.dim * kN : nullptr;
+
+  // activation tiles: 0 u, 1 dout, then z, ypre, delta as present
+  const int iz = 2, iyp = 2 + (gated ? 1 : 0), idl = iyp + (need_yp ? 1 : 0);
+  const int nact = idl + (expl ? 1 : 0);
+
+  // ---- shared memory carve
+  float4* s_ck = reinterpret_cast<float4*>(smem_raw);               // [2][4][G]   checkpoint (state entering the chunk)
+  float* s_red = reinterpret_cast<float*>(s_ck + 2 * 4 * G);        // [nw][32][kRedRow]
+  float* s_part = s_red + nw * 32 * kRedRow;                        // [nw][8][32]  (nw > 1)
+  float* s_el = s_part + (nw > 1 ? nw * kLT * 32 : 0);              // [2][8][G]   delta, softplus'
+  float* s_xf = s_el + 2 * kLT * G;                                 // [8][kXW]    rows as fp32
+  T* s_xr = reinterpret_cast<T*>(s_xf + kLT * kXW);                 // [2][8][kXW] rows as staged
+  T* s_act = s_xr + 2 * kLT * kXW;                                  // [2][nact][8][G]
+
+  const bool dim_vec = (p.dim % kV) == 0;
+  const bool vec_u = dim_vec && aligned16(gu + d0) && (p.u_ts % kV) == 0;
+  const bool vec_do = dim_vec && aligned16(gdo + d0) && (p.dout_ts % kV) == 0;
+  const bool vec_z = gated && dim_vec && aligned16(gz + d0) && (p.z_ts % kV) == 0;
+  const bool vec_yp = need_yp && dim_vec && aligned16(gyp + d0) && (p.out_ts % kV) == 0;
+  const bool vec_dl = expl && dim_vec && aligned16(gdl + d0) && (p.delta_ts % kV) == 0;
+  const bool vec_bc = aligned16(gbc) && (p.bc_ts % kV) == 0;
+  const bool vec_dtr = !expl && (p.flags & BIMAMBA_FLAG_DTR_PADDED) && aligned16(gdtr) && (p.dtr_ts % kV) == 0;
+  const bool vec_ck = gck != nullptr && aligned16(gck);
+
+  auto stage = [&](int c0, int bf) {
+    auto row_of = [&](int i) -> int64_t {
+      const int tau = c0 * kLT + i;
+      return tau < L ? (int64_t)(dir ? (L - 1 - tau) : tau) : (int64_t)-1;
+    };
+    T* sa = s_act + bf * nact * kLT * G;
+    stage_tile(sa, G, gu, p.u_ts, kLT, G, d0, p.dim, vec_u, row_of, tid, G);
+    stage_tile(sa + kLT * G, G, gdo, p.dout_ts, kLT, G, d0, p.dim, vec_do, row_of, tid, G);
+    if (gated) stage_tile(sa + iz * kLT * G, G, gz, p.z_ts, kLT, G, d0, p.dim, vec_z, row_of, tid, G);
+    if (need_yp) stage_tile(sa + iyp * kLT * G, G, gyp, p.out_ts, kLT, G, d0, p.dim, vec_yp, row_of, tid, G);
+    if (expl) stage_tile(sa + idl * kLT * G, G, gdl, p.delta_ts, kLT, G, d0, p.dim, vec_dl, row_of, tid, G);
+    T* sx = s_xr + bf * kLT * kXW;
+    stage_tile(sx, kXW, gbc, p.bc_ts, kLT, 2 * kN, 0, 2 * kN, vec_bc, row_of, tid, G);
+    if (!expl) {
+      const int w = vec_dtr ? 16 : R;
+      stage_tile(sx + 2 * kN, kXW, gdtr, p.dtr_ts, kLT, w, 0, w, vec_dtr, row_of, tid, G);
+    }
+    // this thread's checkpoint: 16 floats = 4 x 16 bytes, into planes [q][G] (conflict-free float4 reads)
+    float4* ck = s_ck + bf * 4 * G + tid;
+    if (vec_ck) {
+      const float* src = gck + ((int64_t)c0 * p.dim + (ok ? d : 0)) * kN;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cp_async16(ck + q * G, src + 4 * q, ok);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gck && ok) {
+          const float* src = gck + ((int64_t)c0 * p.dim + d) * kN + 4 * q;
+          v = make_float4(src[0], src[1], src[2], src[3]);
+        }
+        ck[q * G] = v;
+      }
+    }
+    cp_async_commit();
+  };
+
+  if (nsub > 0) stage(nsub - 1, 0);
+
+  // ---- per-channel constants and accumulators
+  float2 A2[kN / 2], m[kN / 2], dAa[kN / 2];
+  float2 wdt[2 * R4];
+  float bias = 0.f, Dd = 0.f, dDacc = 0.f, dbacc = 0.f;
+#pragma unroll
+  for (int j = 0; j < kN / 2; ++j) {
+    A2[j] = make_float2(0.f, 0.f);
+    m[j] = make_float2(0.f, 0.f);
+    dAa[j] = make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int q = 0; q < 2 * R4; ++q) wdt[q] = make_float2(0.f, 0.f);
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < kN / 2; ++j) {
+      A2[j].x = __ldg(p.A + (int64_t)d * kN + 2 * j) * kLog2e;
+      A2[j].y = __ldg(p.A + (int64_t)d * kN + 2 * j + 1) * kLog2e;
+    }
+    if (p.delta_bias) bias = __ldg(p.delta_bias + d);
+    if (p.D) Dd = __ldg(p.D + d);
+    if (!expl) {
+      float* w = reinterpret_cast<float*>(wdt);
+#pragma unroll
+      for (int r = 0; r < 4 * R4; ++r)
+        if (r < R) w[r] = __ldg(p.Wdt + (int64_t)d * R + r);
+    }
+  }
+  const int v4 = lane & 7, cq = lane >> 3;
+  float* const myred = s_red + (warp * 32 + lane) * kRedRow;
+  const float4* const rdred = reinterpret_cast<const float4*>(s_red + (warp * 32 + cq * 8) * kRedRow) + v4;
+
+  int bf = 0;
+  for (int c0 = nsub - 1; c0 >= 0; --c0, bf ^= 1) {
+    cp_async_wait<0>();
+    __syncthreads();  // chunk c0's tiles are visible; every thread is done with the previous chunk's buffers
+    if (c0 > 0) stage(c0 - 1, bf ^ 1);
+    {
+      const T* sx = s_xr + bf * kLT * kXW;
+      const int valid = 2 * kN + R;
+      for (int e = tid; e < kLT * kXW; e += G) {
+        const int col = e % kXW;
+        s_xf[e] = col < valid ? to_f(sx[e]) : 0.f;
+      }
+    }
+    __syncthreads();
+    const int tau0 = c0 * kLT;
+    const int nvalid = min(kLT, L - tau0);
+    const T* sa = s_act + bf * nact * kLT * G + tid;
+    const float4* ckp = s_ck + bf * 4 * G + tid;
+
+    // ---- re-run the chunk forward from its checkpoint, keeping h[0..6] in registers
+    float2 h[kN / 2], hh[kLT - 1][kN / 2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = ckp[q * G];
+      h[2 * q] = make_float2(v.x, v.y);
+      h[2 * q + 1] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int i = 0; i < kLT; ++i) {
+      const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW);
+      const float u = to_f(sa[i * G]);
+      float draw;
+      if (expl) {
+        draw = bias + to_f(sa[(idl * kLT + i) * G]);
+      } else {
+        float2 acc0 = make_float2(bias, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < R4; ++q) {
+          const float4 x = xr[8 + q];
+          acc0 = __ffma2_rn(wdt[2 * q], make_float2(x.x, x.y), acc0);
+          acc1 = __ffma2_rn(wdt[2 * q + 1], make_float2(x.z, x.w), acc1);
+        }
+        draw = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+      }
+      float delta = draw, sp = 1.f;
+      if (softplus) {
+        delta = softplus_f(draw);
+        sp = draw > 20.f ? 1.f : sigmoid_f(draw);
+      }
+      if (i >= nvalid) delta = 0.f;   // steps past the end of the sequence are the identity
+      s_el[i * G + tid] = delta;
+      s_el[(kLT + i) * G + tid] = sp;
+      const float du = delta * u;
+      const float2 dd = make_float2(delta, delta), duu = make_float2(du, du);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 Bq = xr[q];
+        {
+          const float2 x = __fmul2_rn(dd, A2[2 * q]);
+          const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          h[2 * q] = __ffma2_rn(a, h[2 * q], __fmul2_rn(duu, make_float2(Bq.x, Bq.y)));
+        }
+        {
+          const float2 x = __fmul2_rn(dd, A2[2 * q + 1]);
+          const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          h[2 * q + 1] = __ffma2_rn(a, h[2 * q + 1], __fmul2_rn(duu, make_float2(Bq.z, Bq.w)));
+        }
+      }
+      if (i < kLT - 1) {
+#pragma unroll
+        for (int j = 0; j < kN / 2; ++j) hh[i][j] = h[j];
+      }
+    }
+
+    // ---- reverse recurrence over the chunk:  dh_i = g_i C_i + m_{i+1},  m_i = a_i dh_i
+#pragma unroll
+    for (int i = kLT - 1; i >= 0; --i) {
+      const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW);
+      const float delta = s_el[i * G + tid], sp = s_el[(kLT + i) * G + tid];   // written by this thread
+      const float u = to_f(sa[i * G]);
+      const float dov = to_f(sa[(kLT + i) * G]);
+      const int tau = tau0 + i;
+      const bool live = ok && i < nvalid;
+      const int64_t trow = dir ? (L - 1 - tau) : tau;
+      const int64_t off = trow * p.out_ts + d;
+      float gv = dov;
+      if (gated) {
+        const float zz = to_f(sa[(iz * kLT + i) * G]);
+        const float sg = sigmoid_f(zz);
+        gv = dov * zz * sg;
+        if (need_yp && live) {
+          const float yp = to_f(sa[(iyp * kLT + i) * G]);
+          gdz[off] = from_f<T>(dov * yp * sg * (1.f + zz * (1.f - sg)));
+        }
+      }
+      const float du = delta * u;
+      const float2 dd = make_float2(delta, delta), duu = make_float2(du, du), gg = make_float2(gv, gv);
+      float2 sA = make_float2(0.f, 0.f), sU = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 Bq = xr[q], Cq = xr[4 + q];
+        float4 hpq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i == 0) hpq = ckp[q * G];
+        float2 dBv[2], dCv[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int j = 2 * q + s;
+          const float2 B2 = s ? make_float2(Bq.z, Bq.w) : make_float2(Bq.x, Bq.y);
+          const float2 C2 = s ? make_float2(Cq.z, Cq.w) : make_float2(Cq.x, Cq.y);
+          const float2 x = __fmul2_rn(dd, A2[j]);
+          const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          const float2 dh = __ffma2_rn(gg, C2, m[j]);
+          m[j] = __fmul2_rn(a, dh);
+          const float2 hp = i == 0 ? (s ? make_float2(hpq.z, hpq.w) : make_float2(hpq.x, hpq.y)) : hh[i == 0 ? 0 : i - 1][j];
+          const float2 hc = i == kLT - 1 ? h[j] : hh[i == kLT - 1 ? 0 : i][j];
+          const float2 da = __fmul2_rn(m[j], hp);
+          dAa[j] = __ffma2_rn(da, dd, dAa[j]);
+          sA = __ffma2_rn(da, A2[j], sA);       // sum_n dh a h[t-1] A (x log2e; scaled back below)
+          sU = __ffma2_rn(dh, B2, sU);          // sum_n dh B
+          dBv[s] = __fmul2_rn(dh, duu);
+          dCv[s] = __fmul2_rn(gg, hc);
+        }
+        *reinterpret_cast<float4*>(myred + 4 * q) = make_float4(dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y);
+        *reinterpret_cast<float4*>(myred + kN + 4 * q) = make_float4(dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
+      }
+      const float rA = sA.x + sA.y, rU = sU.x + sU.y;
+      if (live) {
+        const float duv = fmaf(gv, Dd, delta * rU);
+        const float dbl = fmaf(u, rU, rA * kLn2) * sp;
+        gdu[off] = from_f<T>(duv);
+        gdd[off] = from_f<T>(dbl);
+        dDacc = fmaf(gv, u, dDacc);
+        dbacc += dbl;
+      }
+      __syncwarp();
+      {  // column sums over the warp's 32 channels: lane (v4, cq) adds rows cq*8..+7 of columns 4*v4..+3
+        float4 acc = rdred[0];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+          const float4 t = rdred[r * (kRedRow / 4)];
+          acc.x += t.x;
+          acc.y += t.y;
+          acc.z += t.z;
+          acc.w += t.w;
+        }
+        const bool hi = (cq & 2) != 0, odd = (cq & 1) != 0;
+        float kx = hi ? acc.z : acc.x, ky = hi ? acc.w : acc.y;
+        const float sx = hi ? acc.x : acc.z, sy = hi ? acc.y : acc.w;
+        kx += __shfl_xor_sync(kFull, sx, 16);
+        ky += __shfl_xor_sync(kFull, sy, 16);
+        const float keep = odd ? ky : kx, send = odd ? kx : ky;
+        const float val = keep + __shfl_xor_sync(kFull, send, 8);
+        const int v = 4 * v4 + cq;            // column of [dB | dC] this lane now holds
+        if (nw == 1) {
+          if (i < nvalid) partB[trow * pb_ts + v] = val;
+        } else {
+          s_part[(warp * kLT + i) * 32 + v] = val;
+        }
+      }
+      __syncwarp();   // the rows are rewritten by the next step
+    }
+    if (nw > 1) {      // add the warps in fixed order
+      __syncthreads();
+      for (int e = tid; e < kLT * 32; e += G) {
+        const int i = e >> 5, v = e & 31;
+        if (i < nvalid) {
+          float s = 0.f;
+          for (int w = 0; w < nw; ++w) s += s_part[(w * kLT + i) * 32 + v];
+          const int tau = tau0 + i;
+          const int64_t trow = dir ? (L - 1 - tau) : tau;
+          partB[trow * pb_ts + v] = s;
+        }
+      }
+      // the next chunk's first barrier orders these reads before s_part is rewritten
+    }
+  }
+
+  // ---- per-channel partials of this (batch, direction)
+  if (ok) {
+    float* pa = p.dA_part + (bd * p.dim + d) * kN;
+#pragma unroll
+    for (int j = 0; j < kN / 2; ++j) {
+      pa[2 * j] = dAa[j].x;
+      pa[2 * j + 1] = dAa[j].y;
+    }
+    if (p.dD_part) p.dD_part[bd * p.dim + d] = dDacc;
+    if (p.dbias_part) p.dbias_part[bd * p.dim + d] = dbacc;
+  }
+}
+
+static size_t lane_smem_bytes(int G, int esize, bool gated, bool need_yp, bool expl) {
+  const int nw = G / 32;
+  const int nact = 2 + (gated ? 1 : 0) + (need_yp ? 1 : 0) + (expl ? 1 : 0);
+  size_t floats = (size_t)2 * 4 * G * 4 + (size_t)nw * 32 * kRedRow + (nw > 1 ? (size_t)nw * kLT * 32 : 0) +
+                  (size_t)2 * kLT * G + (size_t)kLT * kXW;
+  return floats * 4 + (size_t)2 * kLT * kXW * esize + (size_t)2 * nact * kLT * G * esize;
+}
+
+template <typename T, int kMode>
+static void launch_lane2(const bimamba_scan_desc* d, cudaStream_t st) {
+  const int G = d->group_channels;
+  const bool gated = d->z != nullptr;
+  const size_t smem = lane_smem_bytes(G, (int)sizeof(T), gated, gated && d->dz != nullptr, kMode == 0);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(scan_bwd_lane_kernel<T, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((d->dim + G - 1) / G, d->ndir, d->batch);
+  scan_bwd_lane_kernel<T, kMode><<<grid, G, smem, st>>>(*d);
+}
+
+template <typename T>
+static void launch_lane(const bimamba_scan_desc* d, cudaStream_t st) {
+  const int mode = d->delta ? 0 : (d->dt_rank <= 12 ? 1 : 2);
+  if (mode == 0) launch_lane2<T, 0>(d, st);
+  else if (mode == 1) launch_lane2<T, 1>(d, st);
+  else launch_lane2<T, 2>(d, st);
+}
+
+void launch_bwd_lane(const bimamba_scan_desc* d, cudaStream_t st) {
+  switch (d->io_dtype) {
+    case BIMAMBA_F32: launch_lane<float>(d, st); break;
+    case BIMAMBA_BF16: launch_lane<__nv_bfloat16>(d, st); break;
+    default: launch_lane<__half>(d, st); break;
+  }
+}
+
+}  // namespace bimamba
