@@ -473,7 +473,7 @@ extern "C" int bimamba_selective_scan_bwd(const bimamba_scan_desc* d, bimamba_st
   if (G < kBC || G > kMaxKP * kBC || (G % kBC)) { set_err("backward group_channels must be 32, 64, 96 or 128 (use bimamba_scan_plan)"); return -5; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const char* force = getenv("BIMAMBA_BWD_KERNEL");   // "lane" | "pair": tuning experiments and the parity tests of both
-  const bool lane = force ? force[0] == 'l' : true;
+  const bool lane = (force ? force[0] == 'l' : true) && G == 32;   // the lane kernel is built for one warp per CTA
   if (lane) {
     launch_bwd_lane(d, st);
   } else {
