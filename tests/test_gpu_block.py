@@ -82,6 +82,21 @@ def test_bidirectional_block_fp32_vs_oracle(Bsz, L):
         assert rel(prm.grad, pr[name].grad) < 1e-4, name
 
 
+BWD_VARIANTS = {"lane1": {"BIMAMBA_BWD_KERNEL": "lane", "BIMAMBA_BWD_LANES": "1"},
+                "lane2": {"BIMAMBA_BWD_KERNEL": "lane", "BIMAMBA_BWD_LANES": "2"},
+                "pair": {"BIMAMBA_BWD_KERNEL": "pair"}}
+
+
+@pytest.mark.parametrize("variant", sorted(BWD_VARIANTS))
+@pytest.mark.parametrize("Bsz,L", [(3, 201), (2, 13)])
+def test_bidirectional_block_backward_kernel_variants(variant, Bsz, L, monkeypatch):
+    """The three backward scan kernels (one lane per channel, two lanes per channel, state pairs) forced in turn on
+    the fused block (dt projection inside the kernel): fp32, 1e-4 against the oracle."""
+    for k, v in BWD_VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+    test_bidirectional_block_fp32_vs_oracle(Bsz, L)
+
+
 def test_block_bf16_autocast_vs_oracle():
     """Config-2 numerics: bf16 activations / fp32 state under autocast; oracle in fp64 on the same
     fp32 master weights.  Tolerance 2e-2 relative."""

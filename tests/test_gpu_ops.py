@@ -259,6 +259,21 @@ def test_scan_forward_variants(lanes, dtype, monkeypatch):
         assert max(errs.values()) < TOL[dtype], (lanes, L, D, errs)
 
 
+@pytest.mark.parametrize("variant", ["lane1", "lane2", "pair"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scan_backward_variants(variant, dtype, monkeypatch):
+    """The three backward kernels (one lane per channel with the chunk history in registers; two lanes per channel -
+    small problems; the state-pair kernel) are forced in turn on the same inputs."""
+    monkeypatch.setenv("BIMAMBA_BWD_KERNEL", "pair" if variant == "pair" else "lane")
+    if variant != "pair":
+        monkeypatch.setenv("BIMAMBA_BWD_LANES", variant[-1])
+    for L, D in ((201, 288), (37, 40), (499, 17), (8, 33)):
+        errs = _run_both(2, D, L, dtype, seed=L + D)
+        assert max(errs.values()) < TOL[dtype], (variant, L, D, errs)
+    errs = _run_both(2, 40, 77, dtype, with_z=False, with_D=False, with_bias=False, softplus=False, seed=5)
+    assert max(errs.values()) < TOL[dtype], (variant, errs)
+
+
 @pytest.mark.parametrize("kernel", ["tile", "persist"])
 def test_gemm_nt_kernel_variants(kernel, monkeypatch):
     """Both tcgen05 kernels (one tile per CTA; persistent warp-specialised with two TMEM accumulators) forced in
