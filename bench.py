@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (config 2: 64)")
     ap.add_argument("--frames", type=int, default=201)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scan sweep points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -303,7 +304,10 @@ def run_ours(args, rank, world, local_rank):
 
         def all_reduce():
             return None
-    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4, capturable=True, fused=True)
+    if args.torch_adamw:    # A/B only: the framework's fused multi-tensor AdamW
+        opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4, capturable=True, fused=True)
+    else:                   # this repository's one-launch AdamW (csrc/optim.cu), same update rule
+        opt = bm.FusedAdamW(params, lr=1e-5, weight_decay=1e-4)
 
     B, L = args.batch, args.frames
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -343,7 +347,7 @@ def run_ours(args, rank, world, local_rank):
     zero_grad()
     fwd_loss(x_dev).backward()
     torch.cuda.synchronize()
-    launches_per_step = bm._lib.launch_count
+    launches_per_step = bm._lib.launch_count + (0 if args.torch_adamw else 2)   # + AdamW: step tick + update
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -443,7 +447,8 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args, world), l2="flushed between steps (256 MB write, untimed); per-step CUDA events summed",
                            launch="CUDA-graph replay" if use_graph else "eager", state="fp32", weights="fp32 master, bf16 autocast",
-                           gemm="tcgen05 (this repo)" if bm.ops.TC_GEMM else "cuBLAS"),
+                           gemm="tcgen05 (this repo)" if bm.ops.TC_GEMM else "cuBLAS",
+                           optimizer="torch.optim.AdamW(fused)" if args.torch_adamw else "AdamW, one-launch kernel (this repo)"),
             "clocks": clocks,
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K,

@@ -164,6 +164,22 @@ int bimamba_gemm_tn_splits(int64_t M, int N1, int N2);
 int bimamba_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, float* part, int64_t M, int N1,
                     int N2, int in_dtype, bimamba_stream_t stream);
 
+/* AdamW (torch.optim.AdamW semantics: decoupled weight decay, no amsgrad - the optimizer of src/main.py:453) over a
+ * list of fp32 tensors in one launch.  `table` (device): one entry per tensor; `block_map` (device): nblocks pairs
+ * (tensor index, chunk index), one per CTA, chunk = bimamba_adamw_chunk() elements; `hyper` (device) =
+ * {lr, beta1, beta2, eps, weight_decay}; `state` (device) = {step}: the call first increments the step on the device
+ * (so it can be captured in a CUDA graph and replayed), then updates p, m, v in place. */
+struct bimamba_adamw_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+};
+int bimamba_adamw_chunk(void);
+int bimamba_adamw_step(const struct bimamba_adamw_tensor* table, const int32_t* block_map, int nblocks,
+                       const float* hyper, float* state, bimamba_stream_t stream);
+
 /* Column sums of a (rows, cols) matrix with row stride ld (elements): the bias gradients of the Linear layers.
  * Writes fp32 partials part (nslices, cols), nslices = bimamba_colsum_slices(rows); finish with
  * bimamba_reduce_partials. */

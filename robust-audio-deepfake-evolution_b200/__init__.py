@@ -7,13 +7,14 @@ from .dist import FlatGradBucket, shard_batch
 from .encoder import BiMambaBackend, PN_BiMambas_Encoder
 from .graph import GraphedForward, GraphedTrainStep
 from .mamba_simple import Mamba
+from .optim import FusedAdamW
 from .ops import (BiMambaInnerFn, CausalConv1dFn, SelectiveScanFn, bimamba_inner_fn, causal_conv1d_fn,
                   selective_scan_fn)
 
 __all__ = [
     "Mamba", "PN_BiMambas_Encoder", "BiMambaBackend", "BiMambaInnerFn", "CausalConv1dFn", "SelectiveScanFn",
     "bimamba_inner_fn", "causal_conv1d_fn", "selective_scan_fn", "install_mamba_ssm_shim",
-    "FlatGradBucket", "shard_batch", "GraphedForward", "GraphedTrainStep",
+    "FlatGradBucket", "shard_batch", "GraphedForward", "GraphedTrainStep", "FusedAdamW",
 ]
 
 

@@ -266,3 +266,29 @@ def test_backward_is_bitwise_deterministic():
     for other in runs[1:]:
         for a, b in zip(runs[0], other):
             assert torch.equal(a, b)
+
+
+def test_fused_adamw_matches_torch_adamw():
+    """One-launch AdamW (optim.py / csrc/optim.cu) against torch.optim.AdamW over several steps with changing
+    gradients and a learning-rate change, on tensors of awkward sizes (vector tail, multi-chunk, scalar)."""
+    g = torch.Generator().manual_seed(7)
+    shapes = [(576, 144), (288, 4), (288,), (9000,), (1,), (37, 3)]
+    ref_p = [torch.randn(s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    our_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    ref = torch.optim.AdamW(ref_p, lr=3e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05)
+    ours = bm.FusedAdamW(our_p, lr=3e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05)
+    for it in range(6):
+        if it == 3:
+            for o in (ref, ours):
+                o.param_groups[0]["lr"] = 1e-3
+        for a, b in zip(ref_p, our_p):
+            gr = torch.randn(a.shape, generator=g).cuda()
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        ref.step()
+        ours.step()
+    for a, b in zip(ref_p, our_p):
+        assert rel(b, a) < 1e-6
+    st = ours.state[our_p[0]]
+    assert rel(st["exp_avg"], ref.state[ref_p[0]]["exp_avg"]) < 1e-6
+    assert rel(st["exp_avg_sq"], ref.state[ref_p[0]]["exp_avg_sq"]) < 1e-6
