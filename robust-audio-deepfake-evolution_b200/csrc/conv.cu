@@ -9,6 +9,7 @@
 // kSeg consecutive time steps with a register window of 2K-1 rows, producing both directions from
 // one read of x.  Consecutive threads own consecutive channel vectors, so every load and store of a
 // warp is one contiguous run of the row.
+#include <cstdlib>
 #include <initializer_list>
 
 #include "common.cuh"
@@ -322,6 +323,142 @@ colsum_kernel(const T* __restrict__ x, float* __restrict__ part, int64_t rows, i
   }
 }
 
+// Backward, register-window variant (K = 4, channel vectors of 4): a thread owns 4 consecutive channels and walks one
+// kBwdT-step segment of one batch row plus a K-1 step warm-up, keeping the x window x[tau..tau+3] and the last four
+// g_fwd = dout_fwd silu'(pre_fwd) / g_rev values in registers.  One window serves both directions: it is exactly the
+// taps of pre_fwd[tau+3] and of pre_rev[tau].  Everything is read straight from global memory in 8/16-byte row
+// vectors (consecutive threads = consecutive channels), nothing goes through shared memory: ~65 instructions per
+// (step, channel) against ~230 for the tile kernel above, which stays as the fallback for ragged shapes.
+template <typename T>
+__global__ void __launch_bounds__(kConvThreads)
+conv_bwd_seg_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    const T* __restrict__ dout, T* __restrict__ dx, const T* __restrict__ dz_in, T* __restrict__ dz_out,
+                    float* __restrict__ part, int batch, int ndir, int dim, int L, int64_t x_bs, int64_t x_ts,
+                    int64_t g_bs, int64_t g_ds, int64_t g_ts, int64_t dx_bs, int64_t dx_ts, int silu) {
+  constexpr int K = 4, H = 3, V = 4;
+  const int nvec = dim / V;
+  const int nseg = (L + kBwdT - 1) / kBwdT;
+  const int64_t total = (int64_t)batch * nseg * nvec;
+  const int64_t gid = (int64_t)blockIdx.x * kConvThreads + threadIdx.x;
+  if (gid >= total) return;
+  const int cv = (int)(gid % nvec);
+  const int seg = (int)((gid / nvec) % nseg);
+  const int b = (int)(gid / ((int64_t)nvec * nseg));
+  const int c = cv * V, t0 = seg * kBwdT, t1 = min(L, t0 + kBwdT);
+  const T* xb = x + (int64_t)b * x_bs + c;
+  const T* g0b = dout + (int64_t)b * g_bs + c;
+  const T* g1b = ndir > 1 ? g0b + g_ds : nullptr;
+  const T* z0b = dz_in ? dz_in + (int64_t)b * g_bs + c : nullptr;
+  T* dxb = dx + (int64_t)b * dx_bs + c;
+  T* zob = dz_out ? dz_out + (int64_t)b * dx_bs + c : nullptr;
+
+  float wk[V][K], bs[V], dw[V][K], db[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      wk[v][k] = __ldg(w + (int64_t)(c + v) * K + k);
+      dw[v][k] = 0.f;
+    }
+    bs[v] = bias ? __ldg(bias + c + v) : 0.f;
+    db[v] = 0.f;
+  }
+  // windows: xw[j] = x[tau+j]; gf[j] = g_fwd[tau+j]; gr[j] = g_rev[tau-3+j]   (j = 0..3)
+  float xw[K][V], gf[K][V], gr[K][V];
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      xw[j][v] = 0.f;
+      gf[j][v] = 0.f;
+      gr[j][v] = 0.f;
+    }
+  auto ldx = [&](int t, float (&o)[V]) {
+    if (t >= 0 && t < L) load_row<T, V>(xb + (int64_t)t * x_ts, o);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) o[v] = 0.f;
+    }
+  };
+  // x[t0-3 .. t0-1] (the first window is x[t0-3 .. t0]; its last row is loaded in the loop)
+  ldx(t0 - 3, xw[1]);
+  ldx(t0 - 2, xw[2]);
+  ldx(t0 - 1, xw[3]);
+
+#pragma unroll 4
+  for (int tau = t0 - H; tau < t1; ++tau) {
+    // slide: window becomes x[tau .. tau+3] (the rotation is free once the loop is unrolled by 4)
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j)
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        xw[j][v] = xw[j + 1][v];
+        gf[j][v] = gf[j + 1][v];
+        gr[j][v] = gr[j + 1][v];
+      }
+    ldx(tau + H, xw[K - 1]);
+    const int tf = tau + H;                    // time of the forward-direction value made in this iteration
+    float d0[V], d1[V];
+    const bool f_in = tf < L;                  // tf >= t0 - 0 >= 0 always
+    const bool r_in = tau >= 0;                // tau < t1 <= L always
+    if (f_in) load_row<T, V>(g0b + (int64_t)tf * g_ts, d0);
+    if (r_in && g1b) load_row<T, V>(g1b + (int64_t)tau * g_ts, d1);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float gfn = f_in ? d0[v] : 0.f, grn = (r_in && g1b) ? d1[v] : 0.f;
+      if (silu) {
+        float p0 = bs[v], p1 = bs[v];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          p0 = fmaf(wk[v][k], xw[k][v], p0);           // pre_fwd[tf]  = b + sum_k w[k] x[tf-3+k]
+          p1 = fmaf(wk[v][k], xw[K - 1 - k][v], p1);   // pre_rev[tau] = b + sum_k w[k] x[tau+3-k]
+        }
+        gfn *= silu_grad(p0);
+        grn *= silu_grad(p1);
+      }
+      gf[K - 1][v] = gfn;
+      gr[K - 1][v] = grn;
+      // parameter gradients: each value is counted by the segment that owns its time step
+      const float cf = (tf >= t0 && tf < t1) ? gfn : 0.f;
+      const float cr = tau >= t0 ? grn : 0.f;
+      db[v] += cf + cr;
+#pragma unroll
+      for (int k = 0; k < K; ++k) dw[v][k] = fmaf(cf, xw[k][v], fmaf(cr, xw[K - 1 - k][v], dw[v][k]));
+    }
+    if (tau >= t0) {
+      float o[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          acc = fmaf(wk[v][k], gf[K - 1 - k][v], acc);   // g_fwd[tau+3-k]
+          acc = fmaf(wk[v][k], gr[k][v], acc);           // g_rev[tau-3+k]
+        }
+        o[v] = acc;
+      }
+      store_row<T, V>(dxb + (int64_t)tau * dx_ts, o);
+      if (z0b) {
+        float za[V], zb[V];
+        load_row<T, V>(z0b + (int64_t)tau * g_ts, za);
+        if (ndir > 1) {
+          load_row<T, V>(z0b + g_ds + (int64_t)tau * g_ts, zb);
+#pragma unroll
+          for (int v = 0; v < V; ++v) za[v] += zb[v];
+        }
+        store_row<T, V>(zob + (int64_t)tau * dx_ts, za);
+      }
+    }
+  }
+  float* o = part + ((int64_t)(b * nseg + seg) * dim + c) * (K + 1);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) o[v * (K + 1) + k] = dw[v][k];
+    o[v * (K + 1) + K] = db[v];
+  }
+}
+
 static int conv_bwd_time_tiles(int seqlen) { return seqlen > 0 ? (seqlen + kBwdT - 1) / kBwdT : 1; }
 
 template <typename T, int V>
@@ -415,6 +552,21 @@ extern "C" int bimamba_causal_conv1d_bwd(const void* x, const float* weight, con
   const int ev = dtype == BIMAMBA_F32 ? 4 : 8;
   const int vec = (dim % ev == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(dout) % 16 == 0) &&
                   (x_bs % ev == 0) && (x_ts % ev == 0) && (dout_bs % ev == 0) && (dout_ds % ev == 0) && (dout_ts % ev == 0);
+  // register-window kernel: K = 4 and every row addressable as 4-channel vectors
+  const bool seg4 = width == 4 && getenv("BIMAMBA_CONV_BWD_TILE") == nullptr &&
+                    vec4_ok(dtype, dim, {x, dout, dx, dz_in, dz_out}, {x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts});
+  if (seg4) {
+    const int64_t total = (int64_t)batch * conv_bwd_time_tiles(seqlen) * (dim / 4);
+    const unsigned blocks = (unsigned)((total + kConvThreads - 1) / kConvThreads);
+#define CONV_SEG(T) conv_bwd_seg_kernel<T><<<blocks, kConvThreads, 0, st>>>(reinterpret_cast<const T*>(x), weight, bias, reinterpret_cast<const T*>(dout), reinterpret_cast<T*>(dx), reinterpret_cast<const T*>(dz_in), reinterpret_cast<T*>(dz_out), dwb_part, batch, ndir, dim, seqlen, x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts, silu)
+    if (dtype == BIMAMBA_F32) CONV_SEG(float);
+    else if (dtype == BIMAMBA_BF16) CONV_SEG(__nv_bfloat16);
+    else CONV_SEG(__half);
+#undef CONV_SEG
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) { set_err(cudaGetErrorString(e2)); return (int)e2; }
+    return 0;
+  }
 #define CONV_BWD(T) launch_conv_bwd<T>(x, weight, bias, dout, dx, dz_in, dz_out, dwb_part, batch, ndir, dim, seqlen, width, x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts, silu, vec, st)
   if (dtype == BIMAMBA_F32) CONV_BWD(float);
   else if (dtype == BIMAMBA_BF16) CONV_BWD(__nv_bfloat16);

@@ -83,6 +83,7 @@ def test_bidirectional_block_fp32_vs_oracle(Bsz, L):
 
 
 BWD_VARIANTS = {"lane1": {"BIMAMBA_BWD_KERNEL": "lane", "BIMAMBA_BWD_LANES": "1"},
+                "convtile": {"BIMAMBA_CONV_BWD_TILE": "1"},
                 "lane2": {"BIMAMBA_BWD_KERNEL": "lane", "BIMAMBA_BWD_LANES": "2"},
                 "pair": {"BIMAMBA_BWD_KERNEL": "pair"}}
 
@@ -90,8 +91,9 @@ BWD_VARIANTS = {"lane1": {"BIMAMBA_BWD_KERNEL": "lane", "BIMAMBA_BWD_LANES": "1"
 @pytest.mark.parametrize("variant", sorted(BWD_VARIANTS))
 @pytest.mark.parametrize("Bsz,L", [(3, 201), (2, 13)])
 def test_bidirectional_block_backward_kernel_variants(variant, Bsz, L, monkeypatch):
-    """The three backward scan kernels (one lane per channel, two lanes per channel, state pairs) forced in turn on
-    the fused block (dt projection inside the kernel): fp32, 1e-4 against the oracle."""
+    """The three backward scan kernels (one lane per channel, two lanes per channel, state pairs) and the conv
+    backward's tile fallback forced in turn on the fused block (dt projection inside the kernel, both directions in
+    one launch): fp32, 1e-4 against the oracle."""
     for k, v in BWD_VARIANTS[variant].items():
         monkeypatch.setenv(k, v)
     test_bidirectional_block_fp32_vs_oracle(Bsz, L)

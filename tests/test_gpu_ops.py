@@ -147,6 +147,27 @@ def test_causal_conv1d(dtype, L, act):
     assert rel(bd.grad, br.grad) < tol
 
 
+@pytest.mark.parametrize("D,force_tile", [(20, True), (18, False), (288, True)])
+def test_causal_conv1d_backward_tile_kernel(D, force_tile, monkeypatch):
+    """The shared-memory tile backward (fallback for rows that are not addressable as 4-channel vectors) against the
+    oracle: forced by environment for vector-friendly widths, taken automatically for D = 18."""
+    if force_tile:
+        monkeypatch.setenv("BIMAMBA_CONV_BWD_TILE", "1")
+    g = torch.Generator().manual_seed(D)
+    Bsz, K, L = 2, 4, 77
+    x = torch.randn(Bsz, D, L, generator=g)
+    w = torch.randn(D, K, generator=g) * 0.5
+    b = torch.randn(D, generator=g) * 0.5
+    cot = torch.randn(Bsz, D, L, generator=g)
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    (orc.causal_conv1d_ref(xr, wr, br, "silu") * cot.double()).sum().backward()
+    xd, wd, bd = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    bm.causal_conv1d_fn(xd, wd, bd, activation="silu").backward(cot.cuda())
+    assert rel(xd.grad, xr.grad) < 1e-5
+    assert rel(wd.grad, wr.grad) < 1e-5
+    assert rel(bd.grad, br.grad) < 1e-5
+
+
 @pytest.mark.parametrize("K", [2, 3, 4])
 def test_causal_conv1d_widths_no_bias(K):
     g = torch.Generator().manual_seed(K)
