@@ -425,14 +425,14 @@ def run_ours(args, rank, world, local_rank):
                 tj = json.load(f)
             traffic, traffic_src = tj.get("scan_bwd_dram_bytes_per_launch"), tj.get("source")
         roofline = {
-            "kernel": "scan_bwd_kernel<bf16> (both directions, one launch per layer; the longest kernel of the step)",
+            "kernel": "scan_bwd_lane_kernel<bf16> (both directions, one launch per layer; the longest kernel of the step)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src, "avg_launch_ms": bwd_ms,
             "algorithmic_bytes_per_launch": alg,
             "note": "bf16 IO, (7D+4N)*2 B per frame per direction (SURVEY 8d) x 12864 frames x 2 directions.  The kernel is "
-                    "bound by instruction issue and the shared-memory pipe, not by HBM (DESIGN.md 4.2: ncu issue-active 58 %%, "
-                    "L1TEX data pipe 66 %%, DRAM 5 %%; the config-2 working set also sits in the 126 MB L2), so the HBM "
+                    "latency-bound, not HBM-bound (DESIGN.md 4.2: the Phase-6 grid offers 7.8 warps per SM - 1152 one-warp CTAs; "
+                    "ncu issue-active 40 %%, XU 29 %%, DRAM 9 %%; the config-2 working set also sits in the 126 MB L2), so the HBM "
                     "fraction is low by construction.  scan_fwd (MUFU-bound, DESIGN.md 4.1) avg launch %.4f ms = %.1f GB/s algorithmic"
                     % (fwd_ms, scan_bytes(B * L, 2, 2, False) / (fwd_ms * 1e-3) / 1e9),
             "kernels_ms": {k: round(statistics.mean(v[len(v) // 3:]), 4) for k, v in times.items()},
