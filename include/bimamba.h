@@ -164,6 +164,14 @@ int bimamba_gemm_tn_splits(int64_t M, int N1, int N2);
 int bimamba_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, float* part, int64_t M, int N1,
                     int N2, int in_dtype, bimamba_stream_t stream);
 
+/* Backend head, forward (scoring path): y = LayerNorm(x) over channels; a = softmax over time of (w_att . y + b_att);
+ * features = sum_t a_t y_t; logits = W_cls features + b_cls - src/models/DualStreamSEMamba.py:759-767 in eval mode
+ * (dropout = identity), the score of src/main.py:978-984 being logits[:, 1].  x (batch, seqlen, channels) contiguous
+ * in `dtype`; parameters fp32; features (batch, channels) and logits (batch, nclasses) fp32.  One launch. */
+int bimamba_head_fwd(const void* x, const float* gamma, const float* beta, const float* w_att, const float* b_att,
+                     const float* w_cls, const float* b_cls, float* features, float* logits, int batch, int seqlen,
+                     int channels, int nclasses, float eps, int dtype, bimamba_stream_t stream);
+
 /* AdamW (torch.optim.AdamW semantics: decoupled weight decay, no amsgrad - the optimizer of src/main.py:453) over a
  * list of fp32 tensors in one launch.  `table` (device): one entry per tensor; `block_map` (device): nblocks pairs
  * (tensor index, chunk index), one per CTA, chunk = bimamba_adamw_chunk() elements; `hyper` (device) =

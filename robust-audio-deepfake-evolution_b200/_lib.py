@@ -23,7 +23,7 @@ EXPORTS = (
     "bimamba_selective_scan_fwd", "bimamba_selective_scan_bwd",
     "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_conv_bwd_slices",
     "bimamba_reduce_partials", "bimamba_layernorm_fwd", "bimamba_layernorm_bwd_blocks", "bimamba_layernorm_bwd",
-    "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_gemm_tn_splits", "bimamba_gemm_tn", "bimamba_adamw_chunk", "bimamba_adamw_step", "bimamba_colsum_slices", "bimamba_colsum", "bimamba_pack_weights", "bimamba_cast_transpose",
+    "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_gemm_tn_splits", "bimamba_gemm_tn", "bimamba_adamw_chunk", "bimamba_adamw_step", "bimamba_head_fwd", "bimamba_colsum_slices", "bimamba_colsum", "bimamba_pack_weights", "bimamba_cast_transpose",
 )
 
 
@@ -108,6 +108,8 @@ def load() -> C.CDLL:
         lib.bimamba_colsum.argtypes = [vp, vp, i64, i32, i64, i32, vp]
         lib.bimamba_gemm_nt_block_n_k.restype = i32
         lib.bimamba_gemm_nt_block_n_k.argtypes = [i32, i32]
+        lib.bimamba_head_fwd.restype = i32
+        lib.bimamba_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, i32, vp]
         lib.bimamba_adamw_chunk.restype = i32
         lib.bimamba_adamw_chunk.argtypes = []
         lib.bimamba_adamw_step.restype = i32

@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .mamba_simple import Mamba
-from .ops import feed_forward_fn, layer_norm_fn
+from .ops import feed_forward_fn, head_fwd, layer_norm_fn
 
 
 class PN_BiMambas_Encoder(nn.Module):
@@ -57,6 +57,12 @@ class BiMambaBackend(nn.Module):
 
     def forward(self, f_fused):
         f_fused = self.forward_features(f_fused)
+        if not torch.is_grad_enabled() and not self.training and f_fused.shape[-1] <= 256:
+            # scoring (src/main.py:958-995): norm_f, attention pooling and the classifier in one launch
+            feats, logits = head_fwd(f_fused, self.norm_f.weight, self.norm_f.bias, self.attention_pool.weight,
+                                     self.attention_pool.bias, self.classifier.weight, self.classifier.bias,
+                                     self.norm_f.eps)
+            return feats.to(f_fused.dtype), logits.to(f_fused.dtype)
         f_fused = layer_norm_fn(f_fused, self.norm_f.weight, self.norm_f.bias, self.norm_f.eps,
                                 out_dtype=f_fused.dtype)                                             # :759
         attn = F.softmax(self.attention_pool(f_fused), dim=1)                       # :762

@@ -604,6 +604,28 @@ class LayerNormFn(torch.autograd.Function):
         return dx.view(shape), dgb[0].to(wdt), dgb[1].to(bdt), None, None
 
 
+def head_fwd(x, norm_w, norm_b, att_w, att_b, cls_w, cls_b, eps=1e-5):
+    """Scoring head in one launch (no autograd): LayerNorm -> attention pooling over time -> classifier
+    (src/models/DualStreamSEMamba.py:759-767, eval mode).  x (B, T, C) -> features (B, C) fp32, logits (B, n) fp32."""
+    lib = _lib.load()
+    _require_cuda(x)
+    if x.dtype not in _DT:
+        x = x.float()
+    x = x.contiguous()
+    Bsz, T, C_ = x.shape
+    if T < 1:
+        raise ValueError("head_fwd needs at least one frame")
+    f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+    gw, gb, aw, ab, cw, cb = (f32(t) for t in (norm_w, norm_b, att_w.reshape(-1), att_b, cls_w, cls_b))
+    ncls = cw.shape[0]
+    feats = torch.empty((Bsz, C_), device=x.device, dtype=torch.float32)
+    logits = torch.empty((Bsz, ncls), device=x.device, dtype=torch.float32)
+    with _timed("head_fwd"):
+        _lib.check(lib.bimamba_head_fwd(_ptr(x), _ptr(gw), _ptr(gb), _ptr(aw), _ptr(ab), _ptr(cw), _ptr(cb), _ptr(feats),
+                                        _ptr(logits), Bsz, T, C_, ncls, float(eps), _dt(x), _stream()), "bimamba_head_fwd")
+    return feats, logits
+
+
 def layer_norm_fn(x, weight, bias, eps=1e-5, out_dtype=None):
     """LayerNorm over the last axis; out_dtype defaults to the autocast dtype when autocast is on, else x.dtype."""
     if out_dtype is None:

@@ -323,3 +323,24 @@ def test_gemm_tn_weight_gradient(M, N1, N2, dtype):
     ref = A.double().t() @ B.double()
     assert rel(out, ref) < 1e-5
     assert torch.equal(out, bm.ops.gemm_tn(A, B))
+
+
+@pytest.mark.parametrize("T", [1, 7, 201, 499])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_head_forward_fused(T, dtype):
+    """norm_f -> attention pooling -> classifier in one launch (DualStreamSEMamba.py:759-767, eval) vs fp64."""
+    g = torch.Generator().manual_seed(T)
+    Bsz, C = 5, 144
+    x = (torch.randn(Bsz, T, C, generator=g) * 2 + 0.3).to(dtype)
+    gw, gb = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    aw, ab = torch.randn(1, C, generator=g) * 0.3, torch.randn(1, generator=g)
+    cw, cb = torch.randn(2, C, generator=g) * 0.1, torch.randn(2, generator=g)
+    xd = x.double()
+    y = torch.nn.functional.layer_norm(xd, (C,), gw.double(), gb.double(), 1e-5)
+    a = torch.softmax(y @ aw.double().t() + ab.double(), dim=1)
+    feats_ref = (a.transpose(1, 2) @ y).squeeze(1)
+    logits_ref = feats_ref @ cw.double().t() + cb.double()
+    feats, logits = bm.ops.head_fwd(x.cuda(), gw.cuda(), gb.cuda(), aw.cuda(), ab.cuda(), cw.cuda(), cb.cuda(), 1e-5)
+    assert feats.dtype == torch.float32 and logits.shape == (Bsz, 2)
+    assert rel(feats, feats_ref) < 1e-5
+    assert rel(logits, logits_ref) < 1e-5
