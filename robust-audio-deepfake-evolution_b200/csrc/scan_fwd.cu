@@ -225,6 +225,7 @@ static void launch_fwd(const bimamba_scan_desc* d, cudaStream_t st) {
 
 int check_desc(const bimamba_scan_desc* d, bool bwd);  // api.cu
 void launch_fwd_pair(const bimamba_scan_desc* d, cudaStream_t st);  // scan_fwd2.cu
+void launch_fwd_warp(const bimamba_scan_desc* d, cudaStream_t st);  // scan_fwd1.cu
 
 }  // namespace bimamba
 
@@ -237,14 +238,19 @@ extern "C" int bimamba_selective_scan_fwd(const bimamba_scan_desc* d, bimamba_st
   const int G = d->group_channels;
   if (G < 32 || G > kFwdMaxThreads || (G & 31)) { set_err("forward group_channels must be 32, 64, 96 or 128 (use bimamba_scan_plan)"); return -5; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // One lane per channel is the cheaper instruction stream; with fewer than ~16 warps per SM of such lanes
-  // (the Phase-6 shapes: 36 864 rows) the two-lanes-per-channel variant hides latency better (measured:
-  // 0.097 vs 0.115 ms at batch 64 x 201 frames, 1.59 vs 1.12 ms at 2048 x 256).
+  // Three kernels, same math (forced in turn by tests/test_gpu_ops.py::test_scan_forward_variants):
+  //   3: one lane per channel, one warp per CTA (scan_fwd1.cu) - the Phase-6 sizes (fewer than ~16 warps per SM of
+  //      channel lanes: 0.074 ms per launch at batch 64 x 201 frames, 0.099 for variant 2, 0.115 for variant 1) and fp32 I/O
+  //      (1.04 vs 1.28 ms at 2048 x 256);
+  //   1: one lane per channel, wide CTAs sharing the staged rows - large 16-bit problems (1.06 vs 1.09 ms);
+  //   2: two lanes per channel (scan_fwd2.cu) - kept for experiments.
   const int64_t lanes = (int64_t)d->batch * d->ndir * d->dim;
-  const char* force = getenv("BIMAMBA_FWD_LANES");   // tuning experiments only
-  const bool pair = force ? atoi(force) == 2 : lanes < (int64_t)148 * 16 * 32;
-  if (pair) {
+  const char* force = getenv("BIMAMBA_FWD_LANES");   // tuning experiments and the variant tests
+  const int variant = force ? atoi(force) : ((lanes < (int64_t)148 * 16 * 32 || d->io_dtype == BIMAMBA_F32) ? 3 : 1);
+  if (variant == 2) {
     launch_fwd_pair(d, st);
+  } else if (variant == 3) {
+    launch_fwd_warp(d, st);
   } else {
     switch (d->io_dtype) {
       case BIMAMBA_F32: launch_fwd<float>(d, st); break;

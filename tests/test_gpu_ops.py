@@ -269,11 +269,12 @@ def test_colsum(rows, cols):
     assert rel(out, x.double().sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("lanes", ["1", "2"])
+@pytest.mark.parametrize("lanes", ["1", "2", "3"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_scan_forward_variants(lanes, dtype, monkeypatch):
-    """Both forward kernels (one lane per channel - large problems; two lanes per channel - small problems) are
-    forced in turn on the same inputs; the size-based dispatch must not change results beyond rounding."""
+    """The forward kernels (1: one lane per channel, wide CTAs; 2: two lanes per channel; 3: one lane per channel, one
+    warp per CTA) are forced in turn on the same inputs; the size-based dispatch must not change results beyond
+    rounding."""
     monkeypatch.setenv("BIMAMBA_FWD_LANES", lanes)
     for L, D in ((201, 288), (37, 40), (499, 17)):
         errs = _run_both(2, D, L, dtype, seed=L + D)
