@@ -293,9 +293,11 @@ def run_ours(args, rank, world, local_rank):
             layer.mamba.A_log.add_(0.1 * torch.randn_like(layer.mamba.A_log))
     params = list(model.backbone_layers.parameters())
     if world > 1:
-        bucket = bm.FlatGradBucket(params)      # one flat buffer -> one NCCL all-reduce per step
+        # one flat buffer -> one NCCL all-reduce per step; backward assigns the gradients, one multi-tensor copy packs them
+        bucket = bm.FlatGradBucket(params, accumulate=False)
         zero_grad = bucket.zero
         all_reduce = bucket.all_reduce_mean
+        pack = bucket.pack
     else:                                       # single GPU: no collective, so no bucket; autograd assigns .grad
 
         def zero_grad():
@@ -304,6 +306,7 @@ def run_ours(args, rank, world, local_rank):
 
         def all_reduce():
             return None
+        pack = None
     if args.torch_adamw:    # A/B only: the framework's fused multi-tensor AdamW
         opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4, capturable=True, fused=True)
     else:                   # this repository's one-launch AdamW (csrc/optim.cu), same update rule
@@ -326,7 +329,9 @@ def run_ours(args, rank, world, local_rank):
         def step(x=None):
             return runner.run(x)
     elif use_graph:
-        runner = bm.GraphedTrainStep(fwd_loss, x_dev, zero_grad, None, warmup=3)
+        # multi-GPU: forward, backward and the gradient packing are one graph; the NCCL all-reduce and AdamW are
+        # launched after it (capturing the collective in the same graph hung at 2 GPUs on this stack - r1_history.md)
+        runner = bm.GraphedTrainStep(fwd_loss, x_dev, zero_grad, None, warmup=3, post_backward=pack)
 
         def step(x=None):
             loss = runner.run(x)
@@ -338,6 +343,8 @@ def run_ours(args, rank, world, local_rank):
             zero_grad()
             loss = fwd_loss(x_dev if x is None else x.cuda(non_blocking=True))
             loss.backward()
+            if pack is not None:
+                pack()
             all_reduce()
             opt.step()
             return loss

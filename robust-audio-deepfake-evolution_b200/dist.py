@@ -14,30 +14,66 @@ import torch.distributed as dist
 
 
 class FlatGradBucket:
-    """Views every parameter's .grad into one flat buffer so the all-reduce is a single call."""
+    """One flat buffer for every parameter gradient so the all-reduce is a single call.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], dtype=None):
+    accumulate=True (default): every `.grad` is a view into the buffer and backward accumulates in place - what the
+    reference's double backward (FGM, src/main.py:1077, :1097) and gradient accumulation need; `zero()` clears it.
+    accumulate=False: backward assigns fresh gradients (no per-parameter accumulate kernels), `pack()` gathers them
+    into the buffer with one multi-tensor copy and re-points `.grad` at the views; `zero()` drops the gradients."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], dtype=None, accumulate: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
         self.dtype = dtype or self.params[0].dtype
+        self.accumulate = accumulate
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, device=dev, dtype=self.dtype)
+        self.views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            self.views.append(self.flat[off:off + n].view_as(p))
             off += n
+        if accumulate:
+            self.attach()
+
+    def attach(self):
+        """Point every .grad at its view of the flat buffer."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def zero(self):
-        self.flat.zero_()
+        if self.accumulate:
+            self.flat.zero_()
+        else:
+            for p in self.params:
+                p.grad = None
+
+    def pack(self):
+        """accumulate=False: copy the gradients backward just produced into the flat buffer (one multi-tensor copy;
+        capture-safe) and re-point .grad at the views.  Parameters without a gradient contribute zeros."""
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad.to(self.dtype))
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+        self.attach()
 
     def all_reduce_mean(self, group=None):
-        """Sum over ranks then divide by world size (gradient of the global-batch mean loss)."""
+        """Mean over ranks (gradient of the global-batch mean loss): NCCL averages inside the collective, other
+        backends sum and divide."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
         return self.flat
 
 

@@ -11,7 +11,9 @@ import torch
 
 
 class GraphedTrainStep:
-    """Captures  zero-grad -> forward -> loss -> backward [-> optimizer.step]  for a fixed input shape.
+    """Captures  zero-grad -> forward -> loss -> backward [-> post_backward] [-> optimizer.step]  for a fixed input
+    shape (post_backward: e.g. FlatGradBucket.pack, so a multi-GPU step leaves the graph with the flat gradient ready
+    for the all-reduce).
 
     step_fn(x) must return a scalar loss tensor and must be capture-safe (no host sync).
     `run(x)` copies x (host-pinned or device) into the static input, replays, and returns the static
@@ -19,7 +21,7 @@ class GraphedTrainStep:
 
     def __init__(self, step_fn: Callable[[torch.Tensor], torch.Tensor], example: torch.Tensor,
                  zero_grad: Callable[[], None], optimizer: Optional[torch.optim.Optimizer] = None,
-                 warmup: int = 3):
+                 warmup: int = 3, post_backward: Optional[Callable[[], None]] = None):
         self.static_x = torch.empty_like(example, device="cuda")
         self.static_x.copy_(example)
         self.optimizer = optimizer
@@ -30,6 +32,8 @@ class GraphedTrainStep:
                 zero_grad()
                 loss = step_fn(self.static_x)
                 loss.backward()
+                if post_backward is not None:
+                    post_backward()
                 if optimizer is not None:
                     optimizer.step()
         torch.cuda.current_stream().wait_stream(side)
@@ -39,6 +43,8 @@ class GraphedTrainStep:
             zero_grad()
             self.static_loss = step_fn(self.static_x)
             self.static_loss.backward()
+            if post_backward is not None:
+                post_backward()
             if optimizer is not None:
                 optimizer.step()
 

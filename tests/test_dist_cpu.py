@@ -3,6 +3,7 @@ flat-bucket gradient all-reduce must reproduce the single-process full-batch gra
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -28,12 +29,12 @@ def _make_model():
     return torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 3))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, accumulate=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     model = _make_model()
-    bucket = dmod.FlatGradBucket(model.parameters())
+    bucket = dmod.FlatGradBucket(model.parameters(), accumulate=accumulate)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(10, 12, generator=g)
     y = torch.randn(10, 3, generator=g)
@@ -42,6 +43,10 @@ def _worker(rank, world, port, q):
     # local mean over the shard, weighted so that the average over ranks is the global mean
     loss = ((model(x[lo:hi]) - y[lo:hi]) ** 2).sum() / (10 / world)
     loss.backward()
+    if not accumulate:
+        assert all(p.grad.data_ptr() != v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+        bucket.pack()           # one multi-tensor copy; .grad now views the flat buffer
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
     flat = bucket.all_reduce_mean().clone()
     if rank == 0:
         q.put(flat)
@@ -60,11 +65,14 @@ def test_shard_batch_covers_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_flat_bucket_allreduce_matches_full_batch():
+@pytest.mark.parametrize("accumulate", [True, False])
+def test_flat_bucket_allreduce_matches_full_batch(accumulate):
+    """world_size 2 over gloo: both bucket modes (gradients accumulated into the flat buffer / packed after backward)
+    reproduce the single-process full-batch gradient."""
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, accumulate)) for r in range(2)]
     for p in procs:
         p.start()
     flat = q.get()
