@@ -72,6 +72,28 @@ def test_scan_plan_geometry():
         assert nck == -(-L // 8)
 
 
+def test_host_side_geometry_of_the_new_entry_points():
+    """Launch-geometry helpers are pure host functions: workspace sizes the Python side allocates from."""
+    lib = bm._lib.load()
+    # backward scan: one warp per CTA -> 32-channel groups at every size
+    for rows in (2, 128, 4096):
+        g, ng, _ = bm._lib.scan_plan(201, 288, rows, True)
+        assert (g, ng) == (32, 9)
+    # weight-gradient GEMM: the split over the rows fills about one wave and never exceeds the 64-row blocks
+    for M, n1, n2 in [(12864, 576, 144), (25728, 288, 48), (64, 64, 64), (1, 8, 8), (130, 128, 16)]:
+        ns = lib.bimamba_gemm_tn_splits(M, n1, n2)
+        assert 1 <= ns <= max(1, -(-M // 64)) and ns <= 148
+    assert lib.bimamba_gemm_tn_splits(12864, 576, 144) > 8
+    assert lib.bimamba_adamw_chunk() == 4096
+    assert lib.bimamba_conv_bwd_slices(64, 201, 288) == 64 * 13
+    # argument errors of the new entry points are codes too
+    assert lib.bimamba_gemm_tn(None, 8, None, 8, None, None, 64, 8, 8, 1, None) == -1
+    assert lib.bimamba_adamw_step(None, None, 4, None, None, None) == -1
+    assert lib.bimamba_adamw_step(None, None, 0, None, None, None) == 0
+    assert lib.bimamba_head_fwd(None, None, None, None, None, None, None, None, None, 2, 5, 144, 2, 1e-5, 0, None) == -1
+    assert lib.bimamba_head_fwd(None, None, None, None, None, None, None, None, None, 0, 5, 144, 2, 1e-5, 0, None) == 0
+
+
 def test_python_surface_mirrors_reference_and_has_no_cpu_fallback():
     m = bm.Mamba(144, 16)                                   # DualStreamSEMamba.py:455 positional call
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
