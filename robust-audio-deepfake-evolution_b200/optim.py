@@ -19,7 +19,8 @@ class FusedAdamW(torch.optim.Optimizer):
             raise ValueError("invalid AdamW hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._groups = None      # per param group: device buffers and cached tables
-        self._keep: List[torch.Tensor] = []   # pinned tables a captured graph may still read from
+        self._keep: List[torch.Tensor] = []            # pinned tables of recent eager steps (async copies in flight)
+        self._keep_captured: List[torch.Tensor] = []   # pinned tables a captured graph reads at every replay: never freed
 
     def _build(self):
         lib = _lib.load()
@@ -90,9 +91,12 @@ class FusedAdamW(torch.optim.Optimizer):
                 for i, (p, o) in enumerate(zip(ps, g["offs"])):
                     tab[i] = (p.data_ptr(), gptrs[i], g["m"].data_ptr() + 4 * int(o), g["v"].data_ptr() + 4 * int(o), p.numel())
                 host = torch.from_numpy(tab.reshape(-1)).pin_memory()
-                self._keep.append(host)   # a captured copy node reads this buffer at every replay
-                if len(self._keep) > 64:
-                    del self._keep[:32]
+                if torch.cuda.is_current_stream_capturing():
+                    self._keep_captured.append(host)
+                else:
+                    self._keep.append(host)
+                    if len(self._keep) > 64:
+                        del self._keep[:32]
                 g["table"].copy_(host, non_blocking=True)
                 g["gptrs"] = gptrs
             _lib.check(lib.bimamba_adamw_step(g["table"].data_ptr(), g["bmap"].data_ptr(), g["nblocks"],
