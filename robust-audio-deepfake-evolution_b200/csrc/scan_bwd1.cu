@@ -12,19 +12,25 @@
 // the thread that needs them (no exchange), and dA / dD / dbias accumulate in registers over the whole sequence.
 //   * time is walked in 8-step chunks (the forward's checkpoint interval) from the last to the first.  The chunk is
 //     re-run forward from its checkpoint and the seven intermediate states h[0..6] are KEPT IN REGISTERS (7 x 16):
-//     with every loop unrolled the kernel sits at ~230 registers, i.e. 8 warps per SM - which is all the Phase-6
+//     with every loop unrolled the kernel uses all 255 registers, i.e. 8 warps per SM - which is all the Phase-6
 //     shapes offer anyway (batch 64 x 2 directions x 288 channels = 7.8 warps per SM) - and needs no (L, D, N)
-//     tensor, no shared-memory history and one third of the instructions of the state-pair kernel.
-//   * the decay a[t] = exp2(delta A) is recomputed in the reverse pass (MUFU is not the limiter here: 36 per element
-//     against ~270 issue slots).
+//     tensor, no shared-memory history and less than half the instructions of the state-pair kernel (404 vs 886 per
+//     element).  Keeping part of the history in shared memory was measured slower.
+//   * the decay a[t] = exp2(delta A) is recomputed in the reverse pass (MUFU is not the limiter here: 36 per element,
+//     XU pipe 29 %).
 //   * dB / dC need a sum over channels: per step every lane writes its 32 products to a padded row of shared memory
 //     (8 STS.128, conflict-free), the warp transposes-and-adds them with 8 LDS.128 + packed adds per lane and two
 //     shuffle levels, and lane v ends with column v of the warp's 32-channel sum.  One warp per CTA
-//     (group_channels = 32) needs no block barrier for this and writes the partial row straight to global;
-//     wider CTAs add the warps in fixed order through shared memory.  bimamba_reduce_partials sums the groups:
-//     deterministic, no atomics.
-//   * u, dout, z, ypre tiles [8 x G], the chunk's B|C|dt_r rows and the checkpoint are staged by 16-byte cp.async
-//     into double buffers one chunk ahead.
+//     (group_channels = 32, the shipped configuration) needs no block barrier anywhere and writes the partial row
+//     straight to global; wider CTAs (kNW > 1, experiments) add the warps in fixed order through shared memory.
+//     bimamba_reduce_partials sums the groups: deterministic, no atomics.
+//   * u, dout, z, ypre tiles [8 x G], the chunk's B|C|dt_r rows and the checkpoint are staged by a fixed per-lane
+//     assignment of 16-byte cp.async into double buffers one chunk ahead (generic element-wise staging for tensors
+//     that are not 16-byte friendly).
+//   * all element math is branch-free (the softplus / gate / ypre flags select), and the eight delta chains of a
+//     chunk are computed before the recurrence, so the unrolled steps interleave.
+//   * kSplit = 2 gives a channel to two neighbouring lanes with 8 states each (128 registers, twice the warps); it is
+//     covered by the parity tests but measured slower, so the dispatch never picks it (BIMAMBA_BWD_LANES=2 forces it).
 #include <cstdlib>
 
 #include "common.cuh"
