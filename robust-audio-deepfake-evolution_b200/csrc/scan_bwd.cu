@@ -1,4 +1,7 @@
-// Selective scan, backward, both time directions in one launch.  sm_100a.
+// Selective scan, backward, STATE-PAIR variant (both time directions in one launch).  sm_100a.
+// The default backward kernel is the one-lane-per-channel kernel of scan_bwd1.cu (2.5x fewer instructions); this one
+// is the earlier design, kept as BIMAMBA_BWD_KERNEL=pair and for group widths other than 32, and holds the C entry
+// point that dispatches between the two.
 //
 // Gradients (autograd of src/models/modules/mamba_block.py:80-120, :61):
 //   g = dout * silu(z);  dz = dout * ypre * silu'(z)
@@ -6,8 +9,8 @@
 //   ddelta[t] = sum_n dh a h[t-1] A + u sum_n dh B;  du[t] = g D + delta sum_n dh B
 //   dB[t,n] = sum_d dh delta u;  dC[t,n] = sum_d g h;  dA[n] = sum_t dh a h[t-1] delta
 //
-// Mapping.  The backward needs h[t-1] and a[t] of every step while walking time in reverse, so a
-// thread cannot keep all 16 states of a channel for a whole chunk.  Instead
+// Mapping.  The backward needs h[t-1] and a[t] of every step while walking time in reverse; to stay at 128 registers
+// (16 warps per SM) a thread here does not keep all 16 states of a channel for a whole chunk.  Instead
 //   * a thread owns a PAIR of states (one float2, so the recurrences issue as FMUL2 / FFMA2) of one
 //     channel: lane = 8 * channel_in_warp + pair, a warp works on 4 channels, a CTA (8 warps) on a
 //     "pass" of 32 channels and on `group_channels` = 32 * passes channels of one (batch, dir).
