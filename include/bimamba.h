@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 3
+#define BIMAMBA_ABI_VERSION 4
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -235,6 +235,28 @@ int bimamba_pack_weights(const float* W_in, const float* W_x, const float* W_dt,
 /* dst (rows, cols) = cast(src); dstT (cols, rows) = cast(src)^T: a Linear weight and its data-gradient operand. */
 int bimamba_cast_transpose(const float* src, void* dst, void* dstT, int rows, int cols, int dtype,
                            bimamba_stream_t stream);
+
+/* Exact (erf) GELU of the feed-forward (nn.GELU(), DualStreamSEMamba.py:462) and its backward dx = dy * gelu'(x), over n
+ * contiguous elements of `dtype` (16-byte aligned bases). */
+int bimamba_gelu_fwd(const void* x, void* y, int64_t n, int dtype, bimamba_stream_t stream);
+int bimamba_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, bimamba_stream_t stream);
+
+/* Channel-group sum of the backward scan's [dB | dC] partial rows, written into the first 32 columns of a row matrix:
+ *   out[(g * nrows + r) * out_ld + c] = sum_{i < nparts} part[((g * nparts + i) * nrows + r) * 32 + c],  c < 32
+ * (groups = batch, nparts = ngroups of bimamba_scan_plan, nrows = L * ndir).  `out` is the (batch*L*ndir, 48) operand
+ * [dB | dC | ddt_r | 0] of the x_proj backward (autograd of mamba_block.py:73-75) in out_dtype, so no concatenation is
+ * needed; fixed summation order (deterministic). */
+int bimamba_reduce_rows32(const float* part, void* out, int64_t groups, int nparts, int64_t nrows, int64_t out_ld,
+                          int out_dtype, bimamba_stream_t stream);
+
+/* One launch that turns a block's raw fp32 parameter-gradient buffers into the reference's parameter layouts
+ * (mamba_block.py:22-39): dA_log = dA * A (A = -exp(A_log), :82); x_proj.weight rows [dt_r | B | C] from the repacked
+ * (48, D) [B | C | dt_r | 0]; dt_proj.weight (D, R) = columns 2N..2N+R of dWdt_full (D, 48); out_proj.weight (dm, D) =
+ * sum over the ndir column blocks of dWo2 (dm, ndir*D); conv1d.weight (D, 1, K) and conv1d.bias (D) from dwb (D, K+1). */
+int bimamba_finalize_param_grads(const float* dA, const float* A, const float* dWxp, const float* dWdt_full,
+                                 const float* dWo2, const float* dwb, float* dA_log, float* dWx, float* dWdt,
+                                 float* dWo, float* dconv_w, float* dconv_b, int d_model, int d_inner, int d_state,
+                                 int dt_rank, int ndir, int d_conv, bimamba_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
 FLAG_DTR_PADDED = 2
 FLAG_SILU = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 CHUNK = 16
 
 EXPORTS = (
@@ -24,6 +24,7 @@ EXPORTS = (
     "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_conv_bwd_slices",
     "bimamba_reduce_partials", "bimamba_layernorm_fwd", "bimamba_layernorm_bwd_blocks", "bimamba_layernorm_bwd",
     "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_gemm_tn_splits", "bimamba_gemm_tn", "bimamba_adamw_chunk", "bimamba_adamw_step", "bimamba_head_fwd", "bimamba_colsum_slices", "bimamba_colsum", "bimamba_pack_weights", "bimamba_cast_transpose",
+    "bimamba_gelu_fwd", "bimamba_gelu_bwd", "bimamba_reduce_rows32", "bimamba_finalize_param_grads",
 )
 
 
@@ -120,6 +121,14 @@ def load() -> C.CDLL:
         lib.bimamba_gemm_tn.argtypes = [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, vp]
         lib.bimamba_gemm_nt.restype = i32
         lib.bimamba_gemm_nt.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]
+        lib.bimamba_gelu_fwd.restype = i32
+        lib.bimamba_gelu_fwd.argtypes = [vp, vp, i64, i32, vp]
+        lib.bimamba_gelu_bwd.restype = i32
+        lib.bimamba_gelu_bwd.argtypes = [vp, vp, vp, i64, i32, vp]
+        lib.bimamba_reduce_rows32.restype = i32
+        lib.bimamba_reduce_rows32.argtypes = [vp, vp, i64, i32, i64, i64, i32, vp]
+        lib.bimamba_finalize_param_grads.restype = i32
+        lib.bimamba_finalize_param_grads.argtypes = [vp] * 12 + [i32] * 6 + [vp]
         got = lib.bimamba_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError(f"libbimamba ABI {got} != expected {ABI_VERSION}; rebuild the library")

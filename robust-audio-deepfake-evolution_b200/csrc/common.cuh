@@ -112,6 +112,6 @@ __device__ __forceinline__ void stage_tile(T* __restrict__ sm, int sw, const T* 
   }
 }
 
-__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace bimamba

@@ -1,0 +1,195 @@
+// Small element-wise / layout kernels of the encoder layer's backward and feed-forward, so that a training step contains
+// no framework (ATen) kernels: exact GELU and its derivative (DualStreamSEMamba.py:462), the group sum of the scan's
+// dB|dC partial rows written straight into the x_proj gradient operand, and one "finalize" launch that turns the raw
+// parameter-gradient buffers of a Mamba block into the reference's parameter layouts (mamba_block.py:22-39).  sm_100a.
+#include "common.cuh"
+
+namespace bimamba {
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
+// y = gelu(x) (kBwd = false) or y = g * gelu'(x) (kBwd = true); 16-byte vectors, grid-stride.
+template <typename T, bool kBwd>
+__global__ void __launch_bounds__(256) gelu_kernel(const T* __restrict__ x, const T* __restrict__ g, T* __restrict__ y, int64_t n) {
+  constexpr int kV = 16 / sizeof(T);
+  const int64_t nv = n / kV;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    T xv[kV], gv[kV], yv[kV];
+    *reinterpret_cast<uint4*>(xv) = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    if (kBwd) *reinterpret_cast<uint4*>(gv) = __ldg(reinterpret_cast<const uint4*>(g) + i);
+#pragma unroll
+    for (int k = 0; k < kV; ++k) {
+      const float xf = to_f(xv[k]);
+      yv[k] = from_f<T>(kBwd ? to_f(gv[k]) * gelu_grad_f(xf) : gelu_f(xf));
+    }
+    *(reinterpret_cast<uint4*>(y) + i) = *reinterpret_cast<const uint4*>(yv);
+  }
+  // tail (n not a multiple of the vector width)
+  for (int64_t i = nv * kV + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float xf = to_f(x[i]);
+    y[i] = from_f<T>(kBwd ? to_f(g[i]) * gelu_grad_f(xf) : gelu_f(xf));
+  }
+}
+
+// out[(g * nrows + r) * out_ld + c] = sum_{i < nparts} part[((g * nparts + i) * nrows + r) * 32 + c],  c < 32:
+// the channel-group sum of the backward scan's [dB | dC] partial rows, written into the first 32 columns of the
+// (rows, 48) x_proj gradient operand (row stride out_ld) in the GEMM's dtype.  One thread per 4 columns.
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_rows32_kernel(const float* __restrict__ part, T* __restrict__ out, int64_t groups,
+                                                            int nparts, int64_t nrows, int64_t out_ld) {
+  const int64_t total = groups * nrows * 8;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(e & 7);
+    const int64_t row = e >> 3, g = row / nrows, r = row - g * nrows;
+    const float4* src = reinterpret_cast<const float4*>(part + ((g * nparts) * nrows + r) * 32) + q;
+    float4 s = __ldg(src);
+    for (int i = 1; i < nparts; ++i) {
+      const float4 v = __ldg(src + (int64_t)i * nrows * 8);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    T* dst = out + row * out_ld + 4 * q;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(dst) = s;
+    } else {
+      T v[4] = {from_f<T>(s.x), from_f<T>(s.y), from_f<T>(s.z), from_f<T>(s.w)};
+      *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(v);
+    }
+  }
+}
+
+struct FinalizeArgs {
+  const float* dA;       // (D, N)       sum_t dh a h delta
+  const float* A;        // (D, N)       -exp(A_log)
+  const float* dWxp;     // (48, D)      gradient of the repacked x_proj weight [B | C | dt_r | 0]
+  const float* dWdtf;    // (D, 48)      ddelta^T . [B | C | dt_r | 0] rows: columns 2N .. 2N+R are dt_proj.weight's gradient
+  const float* dWo2;     // (dm, ndir*D) gradient of [W_out | W_out]
+  const float* dwb;      // (D, K+1)     [conv dw | conv dbias]
+  float* dA_log;         // (D, N)
+  float* dWx;            // (R + 2N, D)  rows [dt_r | B | C]
+  float* dWdt;           // (D, R)
+  float* dWo;            // (dm, D)
+  float* dcw;            // (D, K)
+  float* dcb;            // (D)
+  int D, N, R, dm, ndir, K;
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
+  const int D = a.D, N = a.N, R = a.R, dm = a.dm, K = a.K;
+  const int n0 = D * N, n1 = (R + 2 * N) * D, n2 = D * R, n3 = dm * D, n4 = D * K, n5 = D;
+  const int total = n0 + n1 + n2 + n3 + n4 + n5;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int i = e;
+    if (i < n0) { a.dA_log[i] = a.dA[i] * a.A[i]; continue; }                       // A = -exp(A_log): dA_log = dA * A
+    i -= n0;
+    if (i < n1) {                                                                   // [dt_r | B | C] <- [B | C | dt_r]
+      const int r = i / D, c = i - r * D;
+      const int src = r < R ? 2 * N + r : r - R;
+      a.dWx[i] = a.dWxp[src * D + c];
+      continue;
+    }
+    i -= n1;
+    if (i < n2) { const int d = i / R, r = i - d * R; a.dWdt[i] = a.dWdtf[d * kXW + 2 * N + r]; continue; }
+    i -= n2;
+    if (i < n3) {
+      const int r = i / D, c = i - r * D;
+      float s = a.dWo2[(int64_t)r * a.ndir * D + c];
+      if (a.ndir > 1) s += a.dWo2[(int64_t)r * a.ndir * D + D + c];
+      a.dWo[i] = s;
+      continue;
+    }
+    i -= n3;
+    if (i < n4) { const int d = i / K, k = i - d * K; a.dcw[i] = a.dwb[d * (K + 1) + k]; continue; }
+    i -= n4;
+    a.dcb[i] = a.dwb[i * (K + 1) + K];
+  }
+}
+
+}  // namespace bimamba
+
+using namespace bimamba;
+
+static unsigned ew_blocks(int64_t work, int per_block) {
+  int64_t n = (work + per_block - 1) / per_block;
+  if (n < 1) n = 1;
+  return (unsigned)(n > 148 * 16 ? 148 * 16 : n);
+}
+
+extern "C" int bimamba_gelu_fwd(const void* x, void* y, int64_t n, int dtype, bimamba_stream_t stream) {
+  if (n == 0) return 0;
+  if (!x || !y || n < 0 || dtype < 0 || dtype > 2) { set_err("gelu_fwd: bad arguments"); return -1; }
+  if (!aligned16(x) || !aligned16(y)) { set_err("gelu_fwd: operands must be 16-byte aligned"); return -10; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == BIMAMBA_F32)
+    gelu_kernel<float, false><<<ew_blocks(n / 4, 256), 256, 0, st>>>((const float*)x, nullptr, (float*)y, n);
+  else if (dtype == BIMAMBA_BF16)
+    gelu_kernel<__nv_bfloat16, false><<<ew_blocks(n / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, n);
+  else
+    gelu_kernel<__half, false><<<ew_blocks(n / 8, 256), 256, 0, st>>>((const __half*)x, nullptr, (__half*)y, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+extern "C" int bimamba_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, bimamba_stream_t stream) {
+  if (n == 0) return 0;
+  if (!x || !dy || !dx || n < 0 || dtype < 0 || dtype > 2) { set_err("gelu_bwd: bad arguments"); return -1; }
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(dx)) { set_err("gelu_bwd: operands must be 16-byte aligned"); return -10; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == BIMAMBA_F32)
+    gelu_kernel<float, true><<<ew_blocks(n / 4, 256), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, n);
+  else if (dtype == BIMAMBA_BF16)
+    gelu_kernel<__nv_bfloat16, true><<<ew_blocks(n / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, n);
+  else
+    gelu_kernel<__half, true><<<ew_blocks(n / 8, 256), 256, 0, st>>>((const __half*)x, (const __half*)dy, (__half*)dx, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+extern "C" int bimamba_reduce_rows32(const float* part, void* out, int64_t groups, int nparts, int64_t nrows, int64_t out_ld,
+                                     int out_dtype, bimamba_stream_t stream) {
+  if (groups == 0 || nrows == 0) return 0;
+  if (!part || !out || groups < 0 || nparts < 1 || nrows < 0 || out_ld < 32 || out_dtype < 0 || out_dtype > 2) {
+    set_err("reduce_rows32: bad arguments");
+    return -1;
+  }
+  const int es = out_dtype == BIMAMBA_F32 ? 4 : 2;
+  if (!aligned16(part) || (reinterpret_cast<uintptr_t>(out) % (4 * es)) || (out_ld % 4)) {
+    set_err("reduce_rows32: misaligned operands");
+    return -10;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned nb = ew_blocks(groups * nrows * 8, 256);
+  if (out_dtype == BIMAMBA_F32) reduce_rows32_kernel<float><<<nb, 256, 0, st>>>(part, (float*)out, groups, nparts, nrows, out_ld);
+  else if (out_dtype == BIMAMBA_BF16) reduce_rows32_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(part, (__nv_bfloat16*)out, groups, nparts, nrows, out_ld);
+  else reduce_rows32_kernel<__half><<<nb, 256, 0, st>>>(part, (__half*)out, groups, nparts, nrows, out_ld);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+extern "C" int bimamba_finalize_param_grads(const float* dA, const float* A, const float* dWxp, const float* dWdt_full,
+                                            const float* dWo2, const float* dwb, float* dA_log, float* dWx, float* dWdt,
+                                            float* dWo, float* dconv_w, float* dconv_b, int d_model, int d_inner, int d_state,
+                                            int dt_rank, int ndir, int d_conv, bimamba_stream_t stream) {
+  if (!dA || !A || !dWxp || !dWdt_full || !dWo2 || !dwb || !dA_log || !dWx || !dWdt || !dWo || !dconv_w || !dconv_b) {
+    set_err("finalize_param_grads: null operand");
+    return -1;
+  }
+  if (d_model < 1 || d_inner < 1 || d_state != kN || dt_rank < 1 || dt_rank > BIMAMBA_MAX_DT_RANK || ndir < 1 || ndir > 2 || d_conv < 1) {
+    set_err("finalize_param_grads: bad sizes");
+    return -3;
+  }
+  FinalizeArgs a{dA, A, dWxp, dWdt_full, dWo2, dwb, dA_log, dWx, dWdt, dWo, dconv_w, dconv_b, d_inner, d_state, dt_rank, d_model, ndir, d_conv};
+  const int total = d_inner * d_state + (dt_rank + 2 * d_state) * d_inner + d_inner * dt_rank + d_model * d_inner + d_inner * (d_conv + 1);
+  finalize_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}

@@ -117,6 +117,12 @@ class _Fork:
             self.cur.wait_stream(self.side)
 
 
+def _wants_grad(*ts) -> bool:
+    """True when autograd will call backward for these inputs.  Decided in the Python wrappers, not inside
+    Function.forward: grad mode is always off there and ctx.needs_input_grad ignores torch.no_grad()."""
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return None if t is None else t.detach().to(torch.float32).contiguous()
 
@@ -237,11 +243,14 @@ def scan_fwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, wa
 
 
 def scan_bwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, dout, ckpt, ypre,
-                 dtr_padded: bool = False, bc_out_dtype=None, defer: Optional[list] = None):
+                 dtr_padded: bool = False, bc_out_dtype=None, defer: Optional[list] = None,
+                 dbc_rows: Optional[torch.Tensor] = None):
     """Returns (du, ddelta, dz, dbc, dA, dD, dbias): du / ddelta / dz are (B, ndir, L, dim) views of
     (B, L, ndir, dim) storage; dbc is (B, ndir, L, 32) = [dB | dC] likewise; dA (dim, N), dD, dbias (dim).
     With `defer` (a list) the parameter-gradient sums dA / dD / dbias are enqueued on the side stream and the fork is
-    appended to the list: the caller must join() it before using them."""
+    appended to the list: the caller must join() it before using them.
+    With `dbc_rows` (a (B*L*ndir, >= 32) row matrix, rows ordered (b, t, dir)) the group sum of [dB | dC] is written
+    into its first 32 columns and the returned dbc is None."""
     lib = _lib.load()
     Bsz, ndir, L, dim = u.shape
     N = A.shape[1]
@@ -269,10 +278,18 @@ def scan_bwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, do
     with _timed("scan_bwd"):
         _lib.check(lib.bimamba_selective_scan_bwd(C.byref(d), _stream()), "bimamba_selective_scan_bwd")
 
-    dbc = per_dir(Bsz, L, ndir, 2 * N, dev, bc_out_dtype or u.dtype)
-    cols = L * ndir * 2 * N
-    reduce_raw(dbc_part, dbc, groups=Bsz, rows=ngroups, cols=cols, part_gs=ngroups * cols, row_stride=cols,
-               out_gs=cols)
+    if dbc_rows is not None:
+        dbc = None
+        if dbc_rows.shape[0] != Bsz * L * ndir or dbc_rows.stride(1) != 1:
+            raise ValueError("dbc_rows must be a (B*L*ndir, >= 32) row matrix")
+        with _timed("reduce"):
+            _lib.check(lib.bimamba_reduce_rows32(_ptr(dbc_part), _ptr(dbc_rows), Bsz, ngroups, L * ndir, dbc_rows.stride(0),
+                                                 _dt(dbc_rows), _stream()), "bimamba_reduce_rows32")
+    else:
+        dbc = per_dir(Bsz, L, ndir, 2 * N, dev, bc_out_dtype or u.dtype)
+        cols = L * ndir * 2 * N
+        reduce_raw(dbc_part, dbc, groups=Bsz, rows=ngroups, cols=cols, part_gs=ngroups * cols, row_stride=cols,
+                   out_gs=cols)
     dA = torch.empty((dim, N), device=dev, dtype=torch.float32)
     dD = torch.empty((dim,), device=dev, dtype=torch.float32) if D is not None else None
     dbias = torch.empty((dim,), device=dev, dtype=torch.float32) if delta_bias is not None else None
@@ -357,7 +374,7 @@ class SelectiveScanFn(torch.autograd.Function):
     u, delta, z (B, D, L); A (D, N); B, C (B, N, L).  mamba_block.py:80-120, :61."""
 
     @staticmethod
-    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus):
+    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, needs_bwd=True):
         _require_cuda(u, delta, A, B, C, D, z, delta_bias)
         Bshape, Cshape = B.shape, C.shape
         Bm, Cm = _as_bnl(B, "B"), _as_bnl(C, "C")
@@ -369,7 +386,6 @@ class SelectiveScanFn(torch.autograd.Function):
         zl = _cl(z.to(io)).unsqueeze(1) if z is not None else None
         bc = torch.cat([Bm.to(io).transpose(1, 2), Cm.to(io).transpose(1, 2)], dim=2).unsqueeze(1)   # (B, 1, L, 32)
         A32, D32, b32 = _f32c(A), _f32c(D), _f32c(delta_bias)
-        needs_bwd = any(t is not None and t.requires_grad for t in (u, delta, A, B, C, D, z, delta_bias))
         out, ckpt, ypre = scan_fwd_raw(ul, zl, dl, bc, None, None, A32, D32, b32, bool(delta_softplus), needs_bwd)
         ctx.save_for_backward(ul, dl, A32, bc, D32 if D32 is not None else torch.empty(0),
                               zl if zl is not None else torch.empty(0), b32 if b32 is not None else torch.empty(0),
@@ -397,14 +413,15 @@ class SelectiveScanFn(torch.autograd.Function):
         dC = dbc[:, 0, :, N:].transpose(1, 2).to(Cdt).reshape(Cshape)
         return (du[:, 0].transpose(1, 2), ddelta[:, 0].transpose(1, 2).to(deltadt), dA.to(Adt), dB, dC,
                 dD.to(Ddt) if hasD else None, dz[:, 0].transpose(1, 2).to(zdt) if hasz else None,
-                dbias.to(bdt) if hasb else None, None)
+                dbias.to(bdt) if hasb else None, None, None)
 
 
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                       return_last_state=False):
     if return_last_state:
         raise NotImplementedError("return_last_state is not used by the reference path")
-    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus)
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
+                                 _wants_grad(u, delta, A, B, C, D, z, delta_bias))
 
 
 # ----------------------------------------------------------------------------------------
@@ -419,26 +436,34 @@ def _tc_ok(A: torch.Tensor, B: torch.Tensor) -> bool:
             and B.stride(0) % 8 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and A.shape[0] > 0)
 
 
-def gemm_nt(A, B, bias=None, addend=None, out_dtype=None):
+def gemm_nt(A, B, bias=None, addend=None, out_dtype=None, out=None):
     """A (M, K) . B (N, K)^T (+ bias (N) fp32) (+ addend (M, N)) -> (M, N).  bf16 / fp16 operands run on this
     repository's tcgen05 kernel; fp32 operands (the 1e-4 parity mode) stay on the fp32 library GEMM."""
-    out_dtype = out_dtype or A.dtype
+    out_dtype = out_dtype or (out.dtype if out is not None else A.dtype)
     if not _tc_ok(A, B):
         C_ = torch.mm(A, B.t()).to(out_dtype)
         if bias is not None:
             C_ = C_ + bias.to(out_dtype)
         if addend is not None:
             C_ = C_ + addend
+        if out is not None:
+            out.copy_(C_)
+            return out
         return C_
     lib = _lib.load()
     M, K = A.shape
     N = B.shape[0]
-    out = torch.empty((M, N), device=A.device, dtype=out_dtype)
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=out_dtype)
+    elif out.shape != (M, N) or out.dtype != out_dtype or out.stride(1) != 1:
+        raise ValueError("gemm_nt: out must be an (M, N) row matrix of the output dtype with unit column stride")
     if addend is not None:
-        if addend.dtype != out_dtype or addend.shape != out.shape or not addend.is_contiguous():
+        if addend.dtype != out_dtype or addend.shape != out.shape or addend.stride() != out.stride():
             addend = addend.to(out_dtype).contiguous()
+            if out.stride(0) != N:
+                raise ValueError("gemm_nt: addend must share a strided out's layout")
     with _timed("gemm_nt"):
-        _lib.check(lib.bimamba_gemm_nt(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), N, _ptr(bias),
+        _lib.check(lib.bimamba_gemm_nt(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), out.stride(0), _ptr(bias),
                                        _ptr(addend), M, N, K, _dt(A), _dt(out), _stream()), "bimamba_gemm_nt")
     return out
 
@@ -491,6 +516,26 @@ def colsum(x2: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
+    """Exact (erf) GELU of a contiguous tensor, this repository's kernel (DualStreamSEMamba.py:462)."""
+    lib = _lib.load()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    with _timed("gelu"):
+        _lib.check(lib.bimamba_gelu_fwd(_ptr(x), _ptr(y), x.numel(), _dt(x), _stream()), "bimamba_gelu_fwd")
+    return y
+
+
+def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dy * gelu'(x)."""
+    lib = _lib.load()
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    with _timed("gelu"):
+        _lib.check(lib.bimamba_gelu_bwd(_ptr(x), _ptr(dy), _ptr(dx), x.numel(), _dt(x), _stream()), "bimamba_gelu_bwd")
+    return dx
+
+
 # ----------------------------------------------------------------------------------------
 # feed-forward of the encoder layer: Linear(144, 576) -> GELU -> Linear(576, 144) (+ residual)
 # (DualStreamSEMamba.py:460-464, :483-485)
@@ -500,7 +545,7 @@ class FeedForwardFn(torch.autograd.Function):
     tcgen05 GEMM with bias / residual in its epilogue; bias gradients are this repository's column-sum kernel."""
 
     @staticmethod
-    def forward(ctx, x, W1, b1, W2, b2, residual, cdtype):
+    def forward(ctx, x, W1, b1, W2, b2, residual, cdtype, needs_bwd=True):
         _require_cuda(x, W1, b1, W2, b2, residual)
         with torch.autocast("cuda", enabled=False):
             shape = x.shape
@@ -510,11 +555,11 @@ class FeedForwardFn(torch.autograd.Function):
             W1c, W1T = cast_transpose(W1.detach(), cdtype)
             W2c, W2T = cast_transpose(W2.detach(), cdtype)
             h = gemm_nt(x2, W1c, bias=_f32c(b1))                               # :461
-            a = torch.nn.functional.gelu(h)                                    # :462
+            a = gelu_fwd(h)                                                    # :462
             res2 = None if residual is None else residual.detach().reshape(-1, W2.shape[0])
             out_dtype = cdtype if residual is None else residual.dtype
             y = gemm_nt(a, W2c, bias=_f32c(b2), addend=res2, out_dtype=out_dtype)   # :463, :485
-            if any(ctx.needs_input_grad):
+            if needs_bwd:
                 ctx.save_for_backward(x2, h, a, W1T, W2T)
                 ctx.meta = (shape, x.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype, residual is not None)
             return y.view(*shape[:-1], W2.shape[0])
@@ -532,7 +577,7 @@ class FeedForwardFn(torch.autograd.Function):
                 db2 = colsum(g)
                 dW2 = wgrad(g, a)
             da = gemm_nt(g, W2T)
-            dh = torch.ops.aten.gelu_backward(da, h)
+            dh = gelu_bwd(da, h)
             f2.join()
             with _Fork() as f1:                       # first Linear's parameter gradients || its data gradient
                 db1 = colsum(dh)
@@ -540,13 +585,13 @@ class FeedForwardFn(torch.autograd.Function):
             dx = gemm_nt(dh, W1T)
             f1.join()
         return (dx.view(shape).to(xdt), dW1.to(w1dt), db1.to(b1dt), dW2.to(w2dt), db2.to(b2dt),
-                dy if has_res else None, None)
+                dy if has_res else None, None, None)
 
 
 def feed_forward_fn(x, W1, b1, W2, b2, residual=None, compute_dtype=None):
     if compute_dtype is None:
         compute_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
-    return FeedForwardFn.apply(x, W1, b1, W2, b2, residual, compute_dtype)
+    return FeedForwardFn.apply(x, W1, b1, W2, b2, residual, compute_dtype, _wants_grad(x, W1, b1, W2, b2, residual))
 
 
 # ----------------------------------------------------------------------------------------
@@ -557,7 +602,7 @@ class LayerNormFn(torch.autograd.Function):
     reads); statistics in fp32.  x (..., C) fp32 / bf16 / fp16."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, out_dtype):
+    def forward(ctx, x, weight, bias, eps, out_dtype, needs_bwd=True):
         _require_cuda(x, weight, bias)
         lib = _lib.load()
         C_ = x.shape[-1]
@@ -567,7 +612,6 @@ class LayerNormFn(torch.autograd.Function):
         rows = x2.shape[0]
         w32, b32 = _f32c(weight), _f32c(bias)
         y = torch.empty((rows, C_), device=x.device, dtype=out_dtype)
-        needs_bwd = any(ctx.needs_input_grad)
         mean = torch.empty((rows,), device=x.device, dtype=torch.float32) if needs_bwd else None
         rstd = torch.empty((rows,), device=x.device, dtype=torch.float32) if needs_bwd else None
         with _timed("ln_fwd"):
@@ -601,7 +645,7 @@ class LayerNormFn(torch.autograd.Function):
             dgb.zero_()
         else:
             reduce_raw(part, dgb, groups=1, rows=nb, cols=2 * C_, part_gs=0, row_stride=2 * C_, out_gs=0)
-        return dx.view(shape), dgb[0].to(wdt), dgb[1].to(bdt), None, None
+        return dx.view(shape), dgb[0].to(wdt), dgb[1].to(bdt), None, None, None
 
 
 def head_fwd(x, norm_w, norm_b, att_w, att_b, cls_w, cls_b, eps=1e-5):
@@ -630,7 +674,7 @@ def layer_norm_fn(x, weight, bias, eps=1e-5, out_dtype=None):
     """LayerNorm over the last axis; out_dtype defaults to the autocast dtype when autocast is on, else x.dtype."""
     if out_dtype is None:
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
-    return LayerNormFn.apply(x, weight, bias, eps, out_dtype)
+    return LayerNormFn.apply(x, weight, bias, eps, out_dtype, _wants_grad(x, weight, bias))
 
 
 # ----------------------------------------------------------------------------------------
@@ -672,12 +716,6 @@ def cast_transpose(W: torch.Tensor, dtype):
     return dst, dstT
 
 
-def unpack_x_proj_grad(dWp: torch.Tensor, R: int, N: int) -> torch.Tensor:
-    """Gradient of the repacked (48, D) x_proj weight [B | C | dt_r | 0] -> x_proj.weight's own row order
-    [dt_r | B | C] (mamba_block.py:73-75)."""
-    return torch.cat([dWp[2 * N:2 * N + R], dWp[:N], dWp[N:2 * N]], dim=0)
-
-
 class BiMambaInnerFn(torch.autograd.Function):
     """out = M(x) [+ flip(M(flip(x)))] for one Mamba block M with shared weights.
 
@@ -691,7 +729,7 @@ class BiMambaInnerFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bidirectional, cdtype):
+    def forward(ctx, x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bidirectional, cdtype, needs_bwd=True):
         _require_cuda(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out)
         with torch.autocast("cuda", enabled=False):
             Bsz, L, dm = x.shape
@@ -720,7 +758,6 @@ class BiMambaInnerFn(torch.autograd.Function):
             conv_fwd_raw(xs, cw32, cb32, xc, True)                            # :52-55, both directions
             xdbl = gemm_nt(rows2d(xc), Wxp)                                   # (M*ndir, 48)   :73
             xd4 = xdbl.view(Bsz, L, ndir, XW).permute(0, 2, 1, 3)
-            needs_bwd = any(ctx.needs_input_grad)
             y, ckpt, ypre = scan_fwd_raw(xc, z.unsqueeze(1).expand(Bsz, ndir, L, D), None, xd4[..., :2 * N],
                                          xd4[..., 2 * N:], Wd32, A32, D32, bdt32, True, needs_bwd,
                                          dtr_padded=True)                     # :80-120, :61
@@ -748,24 +785,26 @@ class BiMambaInnerFn(torch.autograd.Function):
             xd4 = xdbl.view(Bsz, L, ndir, XW).permute(0, 2, 1, 3)
 
             g2 = dout.to(cd).reshape(M, dm)
+            if g2.stride(1) != 1 or g2.stride(0) != dm:
+                g2 = g2.contiguous()
             # out_proj
             y2 = rows2d(y).view(M, ndir * D)
             with _Fork() as f_out:                                            # out_proj weight gradient || dy, scan
-                dW_out2 = wgrad(g2, y2)                                    # (dm, ndir*D)
-                dW_out = dW_out2[:, :D] + dW_out2[:, D:] if ndir > 1 else dW_out2
+                dW_out2 = wgrad(g2, y2)                                    # (dm, ndir*D), folded over directions at the end
             dy = gemm_nt(g2, WoT)                                             # (M, D), shared by both directions
             # scan (both directions in one launch); dy and z are broadcast over the direction axis
             dyb = dy.view(Bsz, 1, L, D).expand(Bsz, ndir, L, D)
             forks = []                                                        # dA / dD / dbias sums run beside the chain
-            du, ddelta, dz, dbc, dA, dD, dbdt = scan_bwd_raw(
+            dxdbl = torch.empty((M * ndir, XW), device=xz.device, dtype=cd)   # [dB | dC | ddt_r | 0], rows (b, t, dir)
+            du, ddelta, dz, _, dA, dD, dbdt = scan_bwd_raw(
                 xc, z.unsqueeze(1).expand(Bsz, ndir, L, D), None, xd4[..., :2 * N], xd4[..., 2 * N:], Wd32,
-                A32, D32, bdt32, True, dyb, ckpt, ypre, dtr_padded=True, defer=forks)
-            # dt_proj (weight gradient in fp32; the data gradient joins the x_proj row)
+                A32, D32, bdt32, True, dyb, ckpt, ypre, dtr_padded=True, defer=forks, dbc_rows=dxdbl)
+            # dt_proj (weight gradient in fp32; the data gradient is written next to dB | dC: no concatenation)
             dd2 = rows2d(ddelta)                                              # (M*ndir, D)
-            dxdbl = torch.cat([rows2d(dbc), gemm_nt(dd2, WdT)], dim=1)        # (M*ndir, 48) [dB | dC | ddt_r | 0]
+            gemm_nt(dd2, WdT, out=dxdbl[:, 2 * N:])                           # (M*ndir, 16)
             xc2 = rows2d(xc)
             with _Fork() as f_w:                                              # dt_proj / x_proj weight gradients || dxc, conv
-                dW_dt = wgrad(dd2, xdbl)[:, 2 * N:2 * N + R]               # (D, R) of the full-row product
+                dW_dtf = wgrad(dd2, xdbl)                                   # (D, 48): columns 2N..2N+R are dt_proj.weight's
                 dW_xp = wgrad(dxdbl, xc2)                                   # (48, D)
             # x_proj
             dxc = gemm_nt(dxdbl, WxpT, addend=rows2d(du))                     # (M*ndir, D)
@@ -781,11 +820,23 @@ class BiMambaInnerFn(torch.autograd.Function):
             dx = gemm_nt(dxz, WiT).view(Bsz, L, dm)
             for f in (f_out, f_w, f_in, *forks):
                 f.join()
-            dA_log = dA * A32                                                 # A = -exp(A_log)
-            dW_x = unpack_x_proj_grad(dW_xp, R, N)
-        return (dx.to(xdt), dW_in.to(pdt[0]), dwb[:, :K].reshape(cw_shape).to(pdt[1]), dwb[:, K].to(pdt[2]),
+            # one launch: dA_log = dA * A, x_proj rows back to [dt_r | B | C], dt_proj slice, out_proj fold, conv split
+            dev = xz.device
+            f32 = torch.float32
+            dA_log = torch.empty((D, N), device=dev, dtype=f32)
+            dW_x = torch.empty((R + 2 * N, D), device=dev, dtype=f32)
+            dW_dt = torch.empty((D, R), device=dev, dtype=f32)
+            dW_out = torch.empty((dm, D), device=dev, dtype=f32)
+            dcw = torch.empty(cw_shape, device=dev, dtype=f32)
+            dcb = torch.empty((D,), device=dev, dtype=f32)
+            with _timed("finalize"):
+                _lib.check(_lib.load().bimamba_finalize_param_grads(
+                    _ptr(dA), _ptr(A32), _ptr(dW_xp), _ptr(dW_dtf), _ptr(dW_out2), _ptr(dwb), _ptr(dA_log), _ptr(dW_x),
+                    _ptr(dW_dt), _ptr(dW_out), _ptr(dcw), _ptr(dcb), dm, D, N, R, ndir, K, _stream()),
+                    "bimamba_finalize_param_grads")
+        return (dx.to(xdt), dW_in.to(pdt[0]), dcw.to(pdt[1]), dcb.to(pdt[2]),
                 dW_x.to(pdt[3]), dW_dt.to(pdt[4]), dbdt.to(pdt[5]), dA_log.to(pdt[6]), dD.to(pdt[7]),
-                dW_out.to(pdt[8]), None, None)
+                dW_out.to(pdt[8]), None, None, None)
 
 
 def bimamba_inner_fn(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bidirectional=True,
@@ -795,4 +846,4 @@ def bimamba_inner_fn(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out,
     if compute_dtype is None:
         compute_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
     return BiMambaInnerFn.apply(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bool(bidirectional),
-                                compute_dtype)
+                                compute_dtype, _wants_grad(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out))
