@@ -21,7 +21,12 @@ checked by ``tests/test_oracle_golden.py``):
   (``/root/reference/src/models/DualStreamSEMamba.py:445-486``) run in this
   container with ``Mamba`` bound to that ``MambaBlock``;
 * ``compute_eer`` (``/root/reference/src/evaluation.py:126-160``) on seeded
-  score sets.
+  score sets;
+* the reference ``Model`` (``DualStreamSEMamba.py:643-769``) from the two streams'
+  features on - ``DualStreamFusion`` (``:537-637``, both interpolation branches),
+  the 4 backbone layers, ``norm_f``, attention pooling and the classifier
+  (``:697-710``, ``:755-767``) - run through the reference's own ``Model.forward``
+  with only the pretrained WavLM frontend stubbed (``model_tail_*.npz``).
 
 Each function cites the reference lines it follows.  Nothing here is copied:
 the reference is a ``nn.Module`` with a python loop; this is a functional
@@ -220,6 +225,29 @@ def backend_ref(layers, head: Dict[str, Tensor], x: Tensor, eps: float = 1e-5):
     feats = (a.transpose(1, 2) @ x).squeeze(1)                                          # :763
     logits = feats @ head["classifier.weight"].t() + head["classifier.bias"]            # :767
     return feats, logits
+
+
+def fusion_ref(p: Dict[str, Tensor], f_wavlm: Tensor, f_sinc: Tensor, eps: float = 1e-5) -> Tensor:
+    """DualStreamFusion.forward, DualStreamSEMamba.py:580-637 with SELayer :519-531 (eval: dropout = identity).
+    f_wavlm (B, T1, 1024), f_sinc (B, T2, 64) -> (B, T1, out_dim).  Keys as in the module's state_dict
+    (ln_wavlm, ln_sinc, wavlm_proj, sinc_proj, fusion_proj, se_layer.fc.{0,2}, norm)."""
+    fw = F.layer_norm(f_wavlm, (f_wavlm.shape[-1],), p["ln_wavlm.weight"], p["ln_wavlm.bias"], eps)     # :591
+    fs = F.layer_norm(f_sinc, (f_sinc.shape[-1],), p["ln_sinc.weight"], p["ln_sinc.bias"], eps)         # :592
+    fw = fw @ p["wavlm_proj.weight"].t() + p["wavlm_proj.bias"]                                         # :595
+    fs = fs @ p["sinc_proj.weight"].t() + p["sinc_proj.bias"]                                           # :596
+    T1, T2 = fw.shape[1], fs.shape[1]
+    if T1 != T2:                                                                                        # :601-626
+        fs = fs.transpose(1, 2)
+        if T1 / T2 > 4.0:
+            fs = F.interpolate(fs, size=T1, mode="nearest")
+        else:
+            fs = F.interpolate(fs, size=T1, mode="linear", align_corners=False)
+        fs = fs.transpose(1, 2)
+    fused = torch.cat([fw, fs], dim=-1) @ p["fusion_proj.weight"].t() + p["fusion_proj.bias"]           # :629-630
+    se = fused.mean(dim=1)                                                                              # :524-526
+    se = torch.sigmoid(torch.relu(se @ p["se_layer.fc.0.weight"].t()) @ p["se_layer.fc.2.weight"].t())  # :527 (:512-517)
+    fused = fused * se.unsqueeze(1)                                                                     # :528
+    return F.layer_norm(fused, (fused.shape[-1],), p["norm.weight"], p["norm.bias"], eps)               # :636
 
 
 def init_head_params(d_model: int, seed: int = 0, dtype=torch.float32) -> Dict[str, Tensor]:

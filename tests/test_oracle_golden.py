@@ -78,3 +78,54 @@ def test_scan_ref_empty_and_edge():
     y = orc.selective_scan_ref(u, d, -torch.ones(1, 1), torch.tensor([[[3.0]]]), torch.tensor([[[4.0]]]),
                                D=torch.tensor([1.0]))
     assert torch.allclose(y, torch.tensor([[[0.5 * 3 * 2 * 4 + 2.0]]]))
+
+
+def _tail_params(g, dtype=torch.float64, grad=True):
+    P = {k[len("param."):]: torch.tensor(v, dtype=dtype, requires_grad=grad) for k, v in g.items() if k.startswith("param.")}
+    fusion = {k[len("fusion."):]: v for k, v in P.items() if k.startswith("fusion.")}
+    head = {k: v for k, v in P.items() if k.startswith(("norm_f.", "attention_pool.", "classifier."))}
+    nl = 1 + max([int(k.split(".")[1]) for k in P if k.startswith("backbone_layers.")], default=-1)
+    layers = [{k[len(f"backbone_layers.{i}."):]: v for k, v in P.items() if k.startswith(f"backbone_layers.{i}.")}
+              for i in range(nl)]
+    return P, fusion, layers, head
+
+
+def test_fusion_matches_reference_linear_branch(golden_dir):
+    """DualStreamFusion with T1 / T2 <= 4 (linear interpolation, DualStreamSEMamba.py:617-623): the fixture's
+    grad.f_fused is the cotangent, so the fusion block's gradients are reproduced without the backbone."""
+    g = _load(golden_dir, "model_tail_linear.npz")
+    P, fusion, _, _ = _tail_params(g)
+    fw = torch.tensor(g["f_wavlm"], dtype=torch.float64, requires_grad=True)
+    fs = torch.tensor(g["f_sinc"], dtype=torch.float64, requires_grad=True)
+    out = orc.fusion_ref(fusion, fw, fs)
+    assert _rel(out.detach().numpy(), g["f_fused"]) < 1e-12
+    (out * torch.tensor(g["grad.f_fused"])).sum().backward()
+    assert _rel(fw.grad.numpy(), g["grad.f_wavlm"]) < RTOL
+    assert _rel(fs.grad.numpy(), g["grad.f_sinc"]) < 1e-11
+    for k, v in fusion.items():
+        assert _rel(v.grad.numpy(), g["grad.fusion." + k]) < RTOL, k
+
+
+def test_model_tail_matches_reference(golden_dir):
+    """Fusion (nearest branch, the Phase-6 shape 201 vs 29 frames) -> 4 backbone layers -> norm_f -> attention
+    pooling -> classifier against the reference Model.forward run (WavLM frontend stubbed)."""
+    g = _load(golden_dir, "model_tail_nearest.npz")
+    P, fusion, layers, head = _tail_params(g)
+    assert len(layers) == 4
+    fw = torch.tensor(g["f_wavlm"], dtype=torch.float64, requires_grad=True)
+    fs = torch.tensor(g["f_sinc"], dtype=torch.float64, requires_grad=True)
+    fused = orc.fusion_ref(fusion, fw, fs)
+    assert _rel(fused.detach().numpy(), g["f_fused"]) < 1e-12
+    feats, logits = orc.backend_ref(layers, head, fused)
+    assert _rel(feats.detach().numpy(), g["features"]) < 1e-11
+    assert _rel(logits.detach().numpy(), g["logits"]) < 1e-11
+    ((logits * torch.tensor(g["cot_logits"])).sum() + (feats * torch.tensor(g["cot_features"])).sum()).backward()
+    assert _rel(fw.grad.numpy().reshape(-1)[::5], g["grad5.f_wavlm"]) < RTOL
+    assert _rel(fs.grad.numpy(), g["grad.f_sinc"]) < 1e-10
+    for k, v in P.items():
+        if k.startswith("backbone_layers."):
+            assert _rel(v.grad.numpy().reshape(-1)[::5], g["grad5." + k]) < RTOL, k
+        elif k == "attention_pool.bias":      # softmax over time is shift invariant: the true gradient is 0
+            assert np.abs(v.grad.numpy()).max() < 1e-10 and np.abs(g["grad." + k]).max() < 1e-10
+        else:
+            assert _rel(v.grad.numpy(), g["grad." + k]) < RTOL, k
