@@ -167,10 +167,20 @@ int bimamba_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, floa
 /* Backend head, forward (scoring path): y = LayerNorm(x) over channels; a = softmax over time of (w_att . y + b_att);
  * features = sum_t a_t y_t; logits = W_cls features + b_cls - src/models/DualStreamSEMamba.py:759-767 in eval mode
  * (dropout = identity), the score of src/main.py:978-984 being logits[:, 1].  x (batch, seqlen, channels) contiguous
- * in `dtype`; parameters fp32; features (batch, channels) and logits (batch, nclasses) fp32.  One launch. */
+ * in `dtype`; parameters fp32; features (batch, channels) and logits (batch, nclasses) fp32.  One launch.
+ * nclasses = 0 skips the classifier (w_cls, b_cls, logits may be NULL). */
 int bimamba_head_fwd(const void* x, const float* gamma, const float* beta, const float* w_att, const float* b_att,
                      const float* w_cls, const float* b_cls, float* features, float* logits, int batch, int seqlen,
                      int channels, int nclasses, float eps, int dtype, bimamba_stream_t stream);
+
+/* Backward of the pooled features of bimamba_head_fwd (the training head: norm_f + attention pooling under autograd,
+ * DualStreamSEMamba.py:759-763; call bimamba_head_fwd with nclasses = 0 for the forward - dropout and the classifier
+ * act on (batch, channels) outside).  dfeatures (batch, channels) fp32; dx (batch, seqlen, channels) in `dtype`;
+ * part (batch, 4, channels) fp32 = per-utterance rows [dgamma | dbeta | dw_att | (db_att, 0, ...)]: sum over the batch
+ * with bimamba_reduce_partials.  Two launch-free passes over the frames, fixed summation order (deterministic). */
+int bimamba_head_pool_bwd(const void* x, const float* gamma, const float* beta, const float* w_att, const float* b_att,
+                          const float* dfeatures, void* dx, float* part, int batch, int seqlen, int channels, float eps,
+                          int dtype, bimamba_stream_t stream);
 
 /* AdamW (torch.optim.AdamW semantics: decoupled weight decay, no amsgrad - the optimizer of src/main.py:453) over a
  * list of fp32 tensors in one launch.  `table` (device): one entry per tensor; `block_map` (device): nblocks pairs
@@ -203,7 +213,7 @@ int bimamba_layernorm_fwd(const void* x, const float* gamma, const float* beta, 
                           bimamba_stream_t stream);
 
 /* dx (x's dtype) and per-CTA partials dgb_part (nblocks, 2, channels) fp32 = [dgamma | dbeta] with
- * nblocks = bimamba_layernorm_bwd_blocks(rows); reduce with bimamba_reduce_partials.  channels <= 256. */
+ * nblocks = bimamba_layernorm_bwd_blocks(rows); reduce with bimamba_reduce_partials.  channels <= 1024. */
 int bimamba_layernorm_bwd_blocks(int64_t rows);
 int bimamba_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean,
                           const float* rstd, void* dx, float* dgb_part, int64_t rows, int channels,

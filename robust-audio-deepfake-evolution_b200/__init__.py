@@ -5,6 +5,7 @@ through the top-level alias module `bimamba_b200`."""
 from . import _lib
 from .dist import FlatGradBucket, shard_batch
 from .encoder import BiMambaBackend, PN_BiMambas_Encoder
+from .fusion import DualStreamFusion, SELayer
 from .graph import GraphedForward, GraphedTrainStep
 from .mamba_simple import Mamba
 from .optim import FusedAdamW
@@ -14,7 +15,7 @@ from .ops import (BiMambaInnerFn, CausalConv1dFn, SelectiveScanFn, bimamba_inner
 __all__ = [
     "Mamba", "PN_BiMambas_Encoder", "BiMambaBackend", "BiMambaInnerFn", "CausalConv1dFn", "SelectiveScanFn",
     "bimamba_inner_fn", "causal_conv1d_fn", "selective_scan_fn", "install_mamba_ssm_shim",
-    "FlatGradBucket", "shard_batch", "GraphedForward", "GraphedTrainStep", "FusedAdamW",
+    "DualStreamFusion", "SELayer", "FlatGradBucket", "shard_batch", "GraphedForward", "GraphedTrainStep", "FusedAdamW",
 ]
 
 

@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(kLnThreads)
 ln_bwd_kernel(const Tin* __restrict__ x, const Tg* __restrict__ dy, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, Tin* __restrict__ dx,
               float* __restrict__ part /* (gridDim.x, 2, C) */, int64_t rows, int C) {
-  __shared__ float sm[kLnWarps][2][32 * NPL];
+  constexpr bool kWide = NPL > 8;     // wide rows: the warps add into one [2][C] buffer in turn (fixed order)
+  __shared__ float sm[kWide ? 1 : kLnWarps][2][32 * NPL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[NPL], dg[NPL], db[NPL];
 #pragma unroll
@@ -103,18 +104,36 @@ ln_bwd_kernel(const Tin* __restrict__ x, const Tg* __restrict__ dy, const float*
       if (c < C) dr[c] = from_f<Tin>(rs * (dxh[i] - s1 - xh[i] * s2));
     }
   }
+  if constexpr (kWide) {
+    for (int w = 0; w < kLnWarps; ++w) {
+      if (warp == w) {
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    sm[warp][0][lane + 32 * i] = dg[i];
-    sm[warp][1][lane + 32 * i] = db[i];
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 2 * C; e += kLnThreads) {
-    const int k = e / C, c = e - k * C;
-    float s = 0.f;
+        for (int i = 0; i < NPL; ++i) {
+          sm[0][0][lane + 32 * i] = w ? sm[0][0][lane + 32 * i] + dg[i] : dg[i];
+          sm[0][1][lane + 32 * i] = w ? sm[0][1][lane + 32 * i] + db[i] : db[i];
+        }
+      }
+      __syncthreads();
+    }
+    for (int e = threadIdx.x; e < 2 * C; e += kLnThreads) {
+      const int k = e / C, c = e - k * C;
+      part[((int64_t)blockIdx.x * 2 + k) * C + c] = sm[0][k][c];
+    }
+    return;
+  } else {
 #pragma unroll
-    for (int w = 0; w < kLnWarps; ++w) s += sm[w][k][c];
-    part[((int64_t)blockIdx.x * 2 + k) * C + c] = s;
+    for (int i = 0; i < NPL; ++i) {
+      sm[warp][0][lane + 32 * i] = dg[i];
+      sm[warp][1][lane + 32 * i] = db[i];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * C; e += kLnThreads) {
+      const int k = e / C, c = e - k * C;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnWarps; ++w) s += sm[w][k][c];
+      part[((int64_t)blockIdx.x * 2 + k) * C + c] = s;
+    }
   }
 }
 
@@ -144,10 +163,7 @@ static void launch_ln_bwd(const void* x, const void* dy, const float* gamma, con
   Tin* dxp = reinterpret_cast<Tin*>(dx);
   if (C <= 160) ln_bwd_kernel<Tin, Tg, 5><<<blocks, kLnThreads, 0, st>>>(xp, gp, gamma, mean, rstd, dxp, part, rows, C);
   else if (C <= 256) ln_bwd_kernel<Tin, Tg, 8><<<blocks, kLnThreads, 0, st>>>(xp, gp, gamma, mean, rstd, dxp, part, rows, C);
-  else {
-    // 8 warps x 2 x 1024 floats = 64 KB of static shared memory is over the 48 KB static limit
-    set_err("layernorm backward supports C <= 256");
-  }
+  else ln_bwd_kernel<Tin, Tg, kLnMaxPerLane><<<blocks, kLnThreads, 0, st>>>(xp, gp, gamma, mean, rstd, dxp, part, rows, C);
 }
 
 }  // namespace bimamba
@@ -186,7 +202,7 @@ extern "C" int bimamba_layernorm_bwd(const void* x, const void* dy, const float*
                                      int x_dtype, int dy_dtype, bimamba_stream_t stream) {
   if (rows == 0) return 0;
   if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgb_part) { set_err("layernorm bwd: null operand"); return -1; }
-  if (channels < 1 || channels > 256 || rows < 0) { set_err("layernorm backward supports channels 1..256"); return -3; }
+  if (channels < 1 || channels > 32 * kLnMaxPerLane || rows < 0) { set_err("layernorm backward: channels must be 1..1024"); return -3; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   LN_DISPATCH2(x_dtype, dy_dtype, (launch_ln_bwd<T1, T2>(x, dy, gamma, mean, rstd, dx, dgb_part, rows, channels, st)));
   cudaError_t e = cudaGetLastError();

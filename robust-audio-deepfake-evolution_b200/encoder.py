@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .mamba_simple import Mamba
-from .ops import feed_forward_fn, head_fwd, layer_norm_fn
+from .ops import feed_forward_fn, head_fwd, head_pool_fn, layer_norm_fn
 
 
 class PN_BiMambas_Encoder(nn.Module):
@@ -63,9 +63,14 @@ class BiMambaBackend(nn.Module):
                                      self.attention_pool.bias, self.classifier.weight, self.classifier.bias,
                                      self.norm_f.eps)
             return feats.to(f_fused.dtype), logits.to(f_fused.dtype)
-        f_fused = layer_norm_fn(f_fused, self.norm_f.weight, self.norm_f.bias, self.norm_f.eps,
-                                out_dtype=f_fused.dtype)                                             # :759
-        attn = F.softmax(self.attention_pool(f_fused), dim=1)                       # :762
-        features = torch.matmul(attn.transpose(1, 2), f_fused).squeeze(1)           # :763
+        if f_fused.shape[-1] <= 256:
+            # training: norm_f + attention pooling as one kernel forward and one backward (:759-763)
+            features = head_pool_fn(f_fused, self.norm_f.weight, self.norm_f.bias, self.attention_pool.weight,
+                                    self.attention_pool.bias, self.norm_f.eps).to(f_fused.dtype)
+        else:
+            f_fused = layer_norm_fn(f_fused, self.norm_f.weight, self.norm_f.bias, self.norm_f.eps,
+                                    out_dtype=f_fused.dtype)                                         # :759
+            attn = F.softmax(self.attention_pool(f_fused), dim=1)                   # :762
+            features = torch.matmul(attn.transpose(1, 2), f_fused).squeeze(1)       # :763
         features = self.dropout(features)                                           # :764
         return features, self.classifier(features)                                  # :767

@@ -670,6 +670,102 @@ def head_fwd(x, norm_w, norm_b, att_w, att_b, cls_w, cls_b, eps=1e-5):
     return feats, logits
 
 
+class HeadPoolFn(torch.autograd.Function):
+    """features = sum_t softmax_t(w_att . y_t + b_att) y_t with y = LayerNorm(x): norm_f and the attention pooling of the
+    backend head under autograd (DualStreamSEMamba.py:759-763).  x (B, T, C) -> (B, C) fp32; one launch forward, one
+    launch backward (+ the fixed-order sum of the per-utterance parameter-gradient rows)."""
+
+    @staticmethod
+    def forward(ctx, x, norm_w, norm_b, att_w, att_b, eps, needs_bwd=True):
+        _require_cuda(x, norm_w, norm_b, att_w, att_b)
+        lib = _lib.load()
+        xc = x.detach()
+        if xc.dtype not in _DT:
+            xc = xc.float()
+        xc = xc.contiguous()
+        Bsz, T, C_ = xc.shape
+        if T < 1:
+            raise ValueError("head pooling needs at least one frame")
+        gw, gb, aw, ab = _f32c(norm_w), _f32c(norm_b), _f32c(att_w).reshape(-1), _f32c(att_b)
+        feats = torch.empty((Bsz, C_), device=x.device, dtype=torch.float32)
+        with _timed("head_fwd"):
+            _lib.check(lib.bimamba_head_fwd(_ptr(xc), _ptr(gw), _ptr(gb), _ptr(aw), _ptr(ab), None, None, _ptr(feats), None,
+                                            Bsz, T, C_, 0, float(eps), _dt(xc), _stream()), "bimamba_head_fwd")
+        if needs_bwd:
+            ctx.save_for_backward(xc, gw, gb, aw, ab if ab is not None else torch.empty(0))
+            ctx.meta = (eps, x.dtype, norm_w.dtype, norm_b.dtype, att_w.dtype, tuple(att_w.shape),
+                        None if att_b is None else att_b.dtype)
+        return feats
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        xc, gw, gb, aw, ab = ctx.saved_tensors
+        eps, xdt, nwdt, nbdt, awdt, awshape, abdt = ctx.meta
+        ab = ab if ab.numel() else None
+        lib = _lib.load()
+        Bsz, T, C_ = xc.shape
+        df = dfeat.detach().to(torch.float32).contiguous()
+        dx = torch.empty_like(xc)
+        part = torch.empty((Bsz, 4, C_), device=xc.device, dtype=torch.float32)
+        with _timed("head_bwd"):
+            _lib.check(lib.bimamba_head_pool_bwd(_ptr(xc), _ptr(gw), _ptr(gb), _ptr(aw), _ptr(ab), _ptr(df), _ptr(dx),
+                                                 _ptr(part), Bsz, T, C_, float(eps), _dt(xc), _stream()),
+                       "bimamba_head_pool_bwd")
+        sums = torch.empty((4, C_), device=xc.device, dtype=torch.float32)
+        reduce_raw(part, sums, groups=1, rows=Bsz, cols=4 * C_, part_gs=0, row_stride=4 * C_, out_gs=0)
+        return (dx.to(xdt), sums[0].to(nwdt), sums[1].to(nbdt), sums[2].reshape(awshape).to(awdt),
+                None if abdt is None else sums[3, :1].to(abdt), None, None)
+
+
+def head_pool_fn(x, norm_w, norm_b, att_w, att_b, eps=1e-5):
+    return HeadPoolFn.apply(x, norm_w, norm_b, att_w, att_b, eps, _wants_grad(x, norm_w, norm_b, att_w, att_b))
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) (+ addend): an nn.Linear on this repository's kernels - gemm_nt forward and data gradient, the
+    MN-major weight-gradient GEMM and the column-sum kernel for the bias (DualStreamFusion's projections,
+    DualStreamSEMamba.py:565-570).  x (..., K); W (N, K); addend (..., N) in the output's layout."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, addend, cdtype, out_dtype, needs_bwd=True):
+        _require_cuda(x, W, b, addend)
+        with torch.autocast("cuda", enabled=False):
+            shape = x.shape
+            x2 = x.detach().to(cdtype).reshape(-1, shape[-1])
+            if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8):
+                x2 = x2.contiguous()
+            Wc, WT = cast_transpose(W.detach(), cdtype)
+            add2 = None if addend is None else addend.detach().reshape(-1, W.shape[0])
+            y = gemm_nt(x2, Wc, bias=_f32c(b), addend=add2, out_dtype=out_dtype)
+            if needs_bwd:
+                ctx.save_for_backward(x2, WT)
+                ctx.meta = (shape, x.dtype, W.dtype, None if b is None else b.dtype, addend is not None)
+            return y.view(*shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, WT = ctx.saved_tensors
+        shape, xdt, wdt, bdt, has_add = ctx.meta
+        with torch.autocast("cuda", enabled=False):
+            g = dy.reshape(-1, WT.shape[1]).to(x2.dtype)
+            if g.stride(-1) != 1 or g.stride(0) != g.shape[1]:
+                g = g.contiguous()
+            with _Fork() as f:
+                db = colsum(g) if bdt is not None else None
+                dW = wgrad(g, x2)
+            dx = gemm_nt(g, WT)
+            f.join()
+        return (dx.view(shape).to(xdt), dW.to(wdt), None if db is None else db.to(bdt), dy if has_add else None,
+                None, None, None)
+
+
+def linear_fn(x, W, b=None, addend=None, compute_dtype=None, out_dtype=None):
+    if compute_dtype is None:
+        compute_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    out_dtype = out_dtype or (addend.dtype if addend is not None else compute_dtype)
+    return LinearFn.apply(x, W, b, addend, compute_dtype, out_dtype, _wants_grad(x, W, b, addend))
+
+
 def layer_norm_fn(x, weight, bias, eps=1e-5, out_dtype=None):
     """LayerNorm over the last axis; out_dtype defaults to the autocast dtype when autocast is on, else x.dtype."""
     if out_dtype is None:

@@ -294,3 +294,199 @@ def test_fused_adamw_matches_torch_adamw():
     st = ours.state[our_p[0]]
     assert rel(st["exp_avg"], ref.state[ref_p[0]]["exp_avg"]) < 1e-6
     assert rel(st["exp_avg_sq"], ref.state[ref_p[0]]["exp_avg_sq"]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: reference-generated fixtures of the model tail, the reference's own (unfused) forward, fp16 + GradScaler
+# ---------------------------------------------------------------------------------------------------------------------
+def _tail_state(g):
+    return {k[len("param."):]: torch.tensor(v).float() for k, v in g.items() if k.startswith("param.")}
+
+
+@pytest.mark.parametrize("tag,dtype", [("linear", torch.float32), ("nearest", torch.float32), ("nearest", torch.bfloat16)])
+def test_dual_stream_fusion_vs_reference_fixture(golden_dir, tag, dtype):
+    """DualStreamFusion (DualStreamSEMamba.py:537-637, both interpolation branches) against the reference Model run:
+    output and every gradient, with the fixture's grad.f_fused as cotangent."""
+    g = dict(np.load(os.path.join(golden_dir, f"model_tail_{tag}.npz")))
+    fus = bm.DualStreamFusion(1024, 64, 144, reduction=16).cuda().eval()
+    sd = {k[len("fusion."):]: v for k, v in _tail_state(g).items() if k.startswith("fusion.")}
+    fus.load_state_dict(sd, strict=True)
+    fw = torch.tensor(g["f_wavlm"], device="cuda", requires_grad=True)
+    fs = torch.tensor(g["f_sinc"], device="cuda", dtype=torch.float32, requires_grad=True)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    with torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        out = fus(fw, fs)
+    assert out.dtype == torch.float32 and rel(out, g["f_fused"]) < tol
+    out.backward(torch.tensor(g["grad.f_fused"], device="cuda", dtype=torch.float32))
+    if tag == "linear":
+        assert rel(fw.grad, g["grad.f_wavlm"]) < tol
+    else:
+        assert rel(fw.grad.reshape(-1)[::5], g["grad5.f_wavlm"]) < tol
+    assert rel(fs.grad, g["grad.f_sinc"]) < tol
+    for name, p in fus.named_parameters():
+        assert rel(p.grad, g["grad.fusion." + name]) < tol, name
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_model_tail_vs_reference_fixture(golden_dir, dtype):
+    """Fusion -> 4 x PN_BiMambas_Encoder -> norm_f -> attention pooling -> classifier (DualStreamSEMamba.py:697-710,
+    :755-767) against the reference's own Model.forward (fixture; WavLM frontend stubbed): features, logits and every
+    gradient, through the TRAINING head (autograd) and, without grad, through the one-launch scoring head."""
+    g = dict(np.load(os.path.join(golden_dir, "model_tail_nearest.npz")))
+    sd = _tail_state(g)
+    fus = bm.DualStreamFusion(1024, 64, 144).cuda().eval()
+    fus.load_state_dict({k[len("fusion."):]: v for k, v in sd.items() if k.startswith("fusion.")}, strict=True)
+    net = bm.BiMambaBackend(144, 4, 16).cuda().eval()
+    net.load_state_dict({k: v for k, v in sd.items() if not k.startswith("fusion.")}, strict=True)
+    fw = torch.tensor(g["f_wavlm"], device="cuda", requires_grad=True)
+    fs = torch.tensor(g["f_sinc"], device="cuda", dtype=torch.float32, requires_grad=True)
+    # fp32: the north_star's 1e-4.  bf16: 2e-2 is the bar of ONE block; this chains fusion + 4 blocks + head in bf16,
+    # so outputs keep 2e-2 and the gradients that crossed the whole chain get 5e-2.
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    gtol = 1e-4 if dtype == torch.float32 else 5e-2
+    with torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        feats, logits = net(fus(fw, fs))
+    assert rel(feats, g["features"]) < tol and rel(logits, g["logits"]) < tol
+    cl = torch.tensor(g["cot_logits"], device="cuda", dtype=logits.dtype)
+    cf = torch.tensor(g["cot_features"], device="cuda", dtype=feats.dtype)
+    ((logits * cl).sum() + (feats * cf).sum()).float().backward()
+    assert rel(fw.grad.reshape(-1)[::5], g["grad5.f_wavlm"]) < gtol
+    assert rel(fs.grad, g["grad.f_sinc"]) < gtol
+    for name, p in list(net.named_parameters()) + [("fusion." + n, p) for n, p in fus.named_parameters()]:
+        if name == "attention_pool.bias":       # true gradient is 0 (softmax shift invariance)
+            assert float(p.grad.abs().max()) < (1e-5 if dtype == torch.float32 else 1e-3)
+        elif name.startswith("backbone_layers."):
+            assert rel(p.grad.reshape(-1)[::5], g["grad5." + name]) < gtol, name
+        else:
+            assert rel(p.grad, g["grad." + name]) < gtol, name
+    with torch.no_grad(), torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        feats2, logits2 = net(fus(fw, fs))                     # scoring path: head in one launch
+    assert rel(feats2, g["features"]) < tol and rel(logits2, g["logits"]) < tol
+
+
+def test_reference_unfused_forward_through_shim_equals_fused():
+    """The reference's own PN_BiMambas_Encoder.forward (DualStreamSEMamba.py:467-486): two single-direction
+    `mamba_ssm...Mamba` calls, two flips and an add, with nn.LayerNorm / nn.Sequential from torch - run through
+    install_mamba_ssm_shim() - equals this package's fused encoder layer, outputs and every gradient."""
+    import sys
+    bm.install_mamba_ssm_shim()
+    RefMamba = sys.modules["mamba_ssm.modules.mamba_simple"].Mamba
+    assert RefMamba is bm.Mamba
+    torch.manual_seed(11)
+    enc = bm.PN_BiMambas_Encoder(144, 16).cuda()
+    with torch.no_grad():
+        enc.mamba.A_log.add_(0.1 * torch.randn_like(enc.mamba.A_log))
+    x = torch.randn(3, 201, 144, device="cuda")
+    cot = torch.randn(3, 201, 144, device="cuda")
+
+    def reference_forward(m, xin):          # DualStreamSEMamba.py:467-486, verbatim dataflow on the module's attributes
+        residual = xin
+        x_norm = m.norm1(xin)
+        x_f = m.mamba(x_norm)
+        x_b = torch.flip(m.mamba(torch.flip(x_norm, dims=[1])), dims=[1])
+        out = m.norm2(x_f + x_b)
+        return m.feed_forward(out) + residual
+
+    res = []
+    for fn in (lambda xin: enc(xin), lambda xin: reference_forward(enc, xin)):
+        for p in enc.parameters():
+            p.grad = None
+        xi = x.clone().requires_grad_(True)
+        out = fn(xi)
+        out.backward(cot)
+        res.append([out.detach(), xi.grad] + [p.grad.clone() for p in enc.parameters()])
+    for a, b in zip(*res):
+        assert rel(a, b) < 1e-4
+
+
+def test_block_fp16_autocast_with_grad_scaler_vs_oracle():
+    """The reference trains under fp16 autocast + GradScaler (src/main.py:28, :486, :1049, :1077): scaled loss backward,
+    unscale_, clip, step.  Unscaled gradients against the fp64 oracle (fp16 I/O, fp32 state): 5e-3 relative."""
+    p64 = orc.init_mamba_params(144, 16, seed=4, dtype=torch.float64)
+    m = bm.Mamba(144, 16).cuda()
+    _load_mamba(m, {k: v.numpy() for k, v in p64.items()})
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(4, 201, 144, generator=g)
+    cot = torch.randn(4, 201, 144, generator=g) / (4 * 201 * 144)
+    pr = {k: v.float().double().requires_grad_(True) for k, v in p64.items()}
+    xr = x.double().requires_grad_(True)
+    ref = orc.bimamba_ref(pr, xr)
+    (ref * cot.double()).sum().backward()
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 14)
+    opt = torch.optim.SGD(m.parameters(), lr=0.0)
+    xd = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = m.forward_bidirectional(xd)
+        loss = (out.float() * cot.cuda()).sum()
+    assert out.dtype == torch.float16 and rel(out, ref) < 5e-3
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    total = torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=3.0)     # src/main.py:1104
+    assert torch.isfinite(total)
+    scaler.step(opt)
+    scaler.update()
+    assert scaler.get_scale() == 2.0 ** 14                                    # no inf / nan was found
+    clip = min(1.0, 3.0 / (float(total) + 1e-6))
+    for name, prm in m.named_parameters():
+        assert rel(prm.grad, pr[name].grad * clip) < 5e-3, name
+
+
+def test_head_pool_training_vs_oracle():
+    """norm_f + attention pooling under autograd (HeadPoolFn: one launch forward, one backward) against the oracle's
+    composition (DualStreamSEMamba.py:759-763): features and gradients w.r.t. the frames and all four parameters."""
+    head = orc.init_head_params(144, seed=9, dtype=torch.float64)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(5, 201, 144, generator=g)
+    cot = torch.randn(5, 144, generator=g)
+    hp = {k: v.clone().requires_grad_(True) for k, v in head.items()}
+    xr = x.double().requires_grad_(True)
+    xn = torch.nn.functional.layer_norm(xr, (144,), hp["norm_f.weight"], hp["norm_f.bias"], 1e-5)
+    a = torch.softmax(xn @ hp["attention_pool.weight"].t() + hp["attention_pool.bias"], dim=1)
+    f_ref = (a.transpose(1, 2) @ xn).squeeze(1)
+    (f_ref * cot.double()).sum().backward()
+    dev = {k: v.float().cuda().requires_grad_(True) for k, v in head.items()}
+    xd = x.cuda().requires_grad_(True)
+    f = bm.ops.head_pool_fn(xd, dev["norm_f.weight"], dev["norm_f.bias"], dev["attention_pool.weight"],
+                            dev["attention_pool.bias"])
+    assert rel(f, f_ref) < 1e-5
+    f.backward(cot.cuda())
+    assert rel(xd.grad, xr.grad) < 1e-4
+    for k in ("norm_f.weight", "norm_f.bias", "attention_pool.weight"):
+        assert rel(dev[k].grad, hp[k].grad) < 1e-4, k
+    assert float(dev["attention_pool.bias"].grad.abs().max()) < 1e-5
+
+
+def test_eer_identity_full_scoring_set():
+    """SURVEY 8c: ~2 000 utterances x (201, 144).  fp32: scores within 1e-4 and the IDENTICAL EER (rank statistic);
+    bf16 (config 4's headline precision): score max-abs-diff and EER are reported and bounded (2e-2 of the score range,
+    EER within 0.5 % absolute).  The fp64 oracle's python loop runs on the GPU (same code, device-agnostic)."""
+    n_utt, L = 2000, 201
+    layers = [orc.init_encoder_params(144, 16, seed=20 + i) for i in range(4)]
+    head = orc.init_head_params(144, seed=5)
+    g = torch.Generator().manual_seed(2021)
+    feats = torch.randn(n_utt, L, 144, generator=g)
+    labels = (torch.rand(n_utt, generator=g) < 0.1).numpy()
+    with torch.no_grad():
+        lay_d = [{k: v.double().cuda() for k, v in p.items()} for p in layers]
+        head_d = {k: v.double().cuda() for k, v in head.items()}
+        s_ref = torch.cat([orc.backend_ref(lay_d, head_d, feats[i:i + 500].double().cuda())[1][:, 1]
+                           for i in range(0, n_utt, 500)]).cpu().numpy()
+    net = bm.BiMambaBackend(144, 4, 16).cuda().eval()
+    sd = {}
+    for i, p in enumerate(layers):
+        for k, v in p.items():
+            sd[f"backbone_layers.{i}.{k}"] = v
+    sd.update(head)
+    net.load_state_dict(sd, strict=True)
+    eer_ref, _ = orc.compute_eer_ref(s_ref[labels], s_ref[~labels])
+    out = {}
+    for name, dtype in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        with torch.no_grad(), torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+            s = torch.cat([net(feats[i:i + 256].cuda())[1][:, 1].float() for i in range(0, n_utt, 256)])
+        s = s.cpu().numpy().astype(np.float64)
+        eer, _ = orc.compute_eer_ref(s[labels], s[~labels])
+        out[name] = (float(np.abs(s - s_ref).max()), eer)
+    print("EER identity set:", {"ref_eer": eer_ref, **out})
+    scale = max(1.0, float(np.abs(s_ref).max()))
+    assert out["fp32"][0] < 1e-4 * scale and out["fp32"][1] == eer_ref
+    assert out["bf16"][0] < 2e-2 * scale and abs(out["bf16"][1] - eer_ref) < 5e-3

@@ -345,3 +345,54 @@ def test_head_forward_fused(T, dtype):
     assert feats.dtype == torch.float32 and logits.shape == (Bsz, 2)
     assert rel(feats, feats_ref) < 1e-5
     assert rel(logits, logits_ref) < 1e-5
+
+
+def test_scan_long_backward_against_oracle_on_gpu():
+    """Config 5 is 'fwd and bwd' up to L = 8192: every gradient of the scan at L = 8192 against the fp64 oracle (its
+    python loop under autograd, run on the GPU), fp32 I/O 1e-4 and bf16 I/O 2e-2."""
+    for dtype in (torch.float32, torch.bfloat16):
+        u, delta, z, Bm, Cm, A, Dp, bias = _scan_inputs(1, 48, 8192, seed=13, dtype=dtype)
+        names = ["u", "delta", "A", "B", "C", "D", "z", "bias"]
+        cpu = [u, delta, A, Bm, Cm, Dp, z, bias]
+        ref_in = [t.double().cuda().requires_grad_(True) for t in cpu]
+        ref = orc.selective_scan_ref(*ref_in, delta_softplus=True)
+        g = torch.Generator().manual_seed(14)
+        cot = torch.randn(ref.shape, generator=g).to(dtype).cuda()
+        (ref * cot.double()).sum().backward()
+        dev_in = [t.cuda().requires_grad_(True) for t in cpu]
+        out = bm.selective_scan_fn(*dev_in, delta_softplus=True)
+        out.backward(cot)
+        assert rel(out, ref) < TOL[dtype]
+        for n, a, b in zip(names, dev_in, ref_in):
+            assert rel(a.grad, b.grad) < TOL[dtype], (dtype, n)
+
+
+def test_gelu_kernels():
+    g = torch.Generator().manual_seed(1)
+    for dtype, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
+        x = (3 * torch.randn(1000, 577, generator=g)).to(dtype).cuda()
+        dy = torch.randn(1000, 577, generator=g).to(dtype).cuda()
+        xr = x.double().requires_grad_(True)
+        yr = torch.nn.functional.gelu(xr)
+        yr.backward(dy.double())
+        assert rel(bm.ops.gelu_fwd(x), yr) < tol
+        assert rel(bm.ops.gelu_bwd(dy, x), xr.grad) < tol
+
+
+@pytest.mark.parametrize("C_", [1024, 64, 300])
+def test_layernorm_wide_rows(C_):
+    """LayerNorm forward / backward on the fusion block's widths (1024 = WavLM features, 64 = SincNet features)."""
+    g = torch.Generator().manual_seed(C_)
+    x = torch.randn(3, 57, C_, generator=g)
+    w = 1 + 0.1 * torch.randn(C_, generator=g)
+    b = 0.1 * torch.randn(C_, generator=g)
+    cot = torch.randn(3, 57, C_, generator=g)
+    ref_in = [t.double().requires_grad_(True) for t in (x, w, b)]
+    ref = torch.nn.functional.layer_norm(ref_in[0], (C_,), ref_in[1], ref_in[2], 1e-5)
+    ref.backward(cot.double())
+    dev_in = [t.cuda().requires_grad_(True) for t in (x, w, b)]
+    out = bm.ops.layer_norm_fn(*dev_in, 1e-5)
+    out.backward(cot.cuda())
+    assert rel(out, ref) < 1e-5
+    for a, r in zip(dev_in, ref_in):
+        assert rel(a.grad, r.grad) < 1e-5
