@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scan sweep points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="overlap", choices=["overlap", "graph", "eager"],
+                    help="N > 1: gradient all-reduce per encoder layer inside the step graph, overlapping the remaining "
+                         "backward (default); one all-reduce inside the graph; or launched after the graph (round 1)")
     return ap.parse_args()
 
 
@@ -293,11 +296,16 @@ def run_ours(args, rank, world, local_rank):
             layer.mamba.A_log.add_(0.1 * torch.randn_like(layer.mamba.A_log))
     params = list(model.backbone_layers.parameters())
     if world > 1:
-        # one flat buffer -> one NCCL all-reduce per step; backward assigns the gradients, one multi-tensor copy packs them
+        # one flat buffer; backward assigns the gradients, multi-tensor copies pack them, NCCL averages them
         bucket = bm.FlatGradBucket(params, accumulate=False)
         zero_grad = bucket.zero
         all_reduce = bucket.all_reduce_mean
         pack = bucket.pack
+        if args.comm == "overlap":      # one collective per encoder layer, issued when that layer's backward is done
+            bucket.enable_overlap([list(layer.parameters()) for layer in model.backbone_layers])
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)           # communicator set-up outside any capture
+        torch.cuda.synchronize()
     else:                                       # single GPU: no collective, so no bucket; autograd assigns .grad
 
         def zero_grad():
@@ -328,9 +336,21 @@ def run_ours(args, rank, world, local_rank):
 
         def step(x=None):
             return runner.run(x)
+    elif use_graph and args.comm != "eager":
+        # multi-GPU: forward, backward, the per-layer gradient collectives (parallel branches that overlap the remaining
+        # backward) and AdamW are ONE graph
+        if args.comm == "overlap":
+            post = bucket.finish_overlap
+        else:
+            def post():
+                pack()
+                all_reduce()
+        runner = bm.GraphedTrainStep(fwd_loss, x_dev, zero_grad, opt, warmup=3, post_backward=post)
+
+        def step(x=None):
+            return runner.run(x)
     elif use_graph:
-        # multi-GPU: forward, backward and the gradient packing are one graph; the NCCL all-reduce and AdamW are
-        # launched after it (capturing the collective in the same graph hung at 2 GPUs on this stack - r1_history.md)
+        # round-1 arrangement: the NCCL all-reduce and AdamW launched after the graph
         runner = bm.GraphedTrainStep(fwd_loss, x_dev, zero_grad, None, warmup=3, post_backward=pack)
 
         def step(x=None):
@@ -343,9 +363,12 @@ def run_ours(args, rank, world, local_rank):
             zero_grad()
             loss = fwd_loss(x_dev if x is None else x.cuda(non_blocking=True))
             loss.backward()
-            if pack is not None:
-                pack()
-            all_reduce()
+            if world > 1 and args.comm == "overlap":
+                bucket.finish_overlap()
+            else:
+                if pack is not None:
+                    pack()
+                all_reduce()
             opt.step()
             return loss
 
@@ -353,6 +376,8 @@ def run_ours(args, rank, world, local_rank):
     bm._lib.launch_count = 0
     zero_grad()
     fwd_loss(x_dev).backward()
+    if world > 1 and args.comm == "overlap":
+        bucket.finish_overlap()
     torch.cuda.synchronize()
     launches_per_step = bm._lib.launch_count + (0 if args.torch_adamw else 2)   # + AdamW: step tick + update
 
@@ -387,7 +412,7 @@ def run_ours(args, rank, world, local_rank):
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
 
     # ---- end to end: pinned host input -> H2D -> step -> loss.item() every step ----
-    pipelined = use_graph and world == 1
+    pipelined = use_graph and (world == 1 or args.comm != "eager")
     for _ in range(2):
         float(step(x_host).detach())
     barrier()
@@ -415,6 +440,8 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = load_peaks()
         timer = EventTimer()
         bm._lib.kernel_timer = timer
+        if world > 1 and args.comm == "overlap":
+            bucket.disable_overlap()        # rank 0 alone runs this instrumented pass: no collectives
         for _ in range(3):
             flush.zero_()
             zero_grad()
@@ -455,6 +482,9 @@ def run_ours(args, rank, world, local_rank):
             "config": dict(workload_config(args, world), l2="flushed between steps (256 MB write, untimed); per-step CUDA events summed",
                            launch="CUDA-graph replay" if use_graph else "eager", state="fp32", weights="fp32 master, bf16 autocast",
                            gemm="tcgen05 (this repo)" if bm.ops.TC_GEMM else "cuBLAS",
+                           comm=(None if world == 1 else {"overlap": "NCCL all-reduce (AVG) per encoder layer inside the step "
+                                 "graph, overlapping the remaining backward", "graph": "one NCCL all-reduce inside the step graph",
+                                 "eager": "one NCCL all-reduce after the graph"}[args.comm]),
                            optimizer="torch.optim.AdamW(fused)" if args.torch_adamw else "AdamW, one-launch kernel (this repo)"),
             "clocks": clocks,
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
@@ -472,7 +502,17 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        # a CUDA graph that holds captured NCCL work keeps the communicator busy: release it before tearing the
+        # process group down, and never let a stuck teardown outlive the measurement (the JSON line is already out)
+        if use_graph:
+            runner.graph.reset()
+        guard = threading.Timer(20.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
         dist.destroy_process_group()
+        guard.cancel()
 
 
 def main():

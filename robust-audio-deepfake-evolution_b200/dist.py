@@ -22,6 +22,8 @@ class FlatGradBucket:
     into the buffer with one multi-tensor copy and re-points `.grad` at the views; `zero()` drops the gradients."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], dtype=None, accumulate: bool = True):
+        self._hooks = []
+        self._segments = None
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -64,6 +66,76 @@ class FlatGradBucket:
         if src:
             torch._foreach_copy_(dst, src)
         self.attach()
+
+    # ---- overlap: one collective per segment, launched as soon as backward has produced the segment's gradients -------
+    def enable_overlap(self, segments: List[List[torch.nn.Parameter]], group=None):
+        """accumulate=False only.  `segments` partitions the parameters (e.g. one list per encoder layer, in any order);
+        a post-accumulate hook on every parameter counts arrivals and, when a segment is complete, packs it into its
+        slice of the flat buffer and all-reduces that slice on a communication stream, so the collectives of layers
+        N..2 run under the backward of layers N-1..1.  Call `finish_overlap()` after backward (GraphedTrainStep's
+        post_backward): it joins the communication stream and re-points .grad at the views.  Under CUDA-graph capture
+        the hooks run once, at capture: the collectives become parallel branches of the captured graph."""
+        if self.accumulate:
+            raise ValueError("overlap needs accumulate=False (gradients are packed per segment)")
+        index = {id(p): i for i, p in enumerate(self.params)}
+        seen = set()
+        self._segments = []
+        for seg in segments:
+            idx = sorted(index[id(p)] for p in seg if id(p) in index)
+            if not idx:
+                continue
+            if idx != list(range(idx[0], idx[-1] + 1)) or seen & set(idx):
+                raise ValueError("every segment must be a contiguous, disjoint run of the bucket's parameter order")
+            seen |= set(idx)
+            lo = sum(self.params[i].numel() for i in range(idx[0]))
+            n = sum(self.params[i].numel() for i in idx)
+            self._segments.append({"idx": idx, "flat": self.flat[lo:lo + n], "count": 0})
+        if seen != set(range(len(self.params))):
+            raise ValueError("segments must cover every parameter of the bucket")
+        self._group = group
+        self._comm = torch.cuda.Stream(device=self.flat.device) if self.flat.is_cuda else None   # CPU (gloo tests): inline
+        seg_of = {i: s for s in self._segments for i in s["idx"]}
+        for i, p in enumerate(self.params):
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(seg_of[i])))
+
+    def _make_hook(self, seg):
+        def hook(_param):
+            seg["count"] += 1
+            if seg["count"] < len(seg["idx"]):
+                return
+            seg["count"] = 0
+            def pack_and_reduce():
+                src = [self.params[i].grad.to(self.dtype) for i in seg["idx"]]
+                torch._foreach_copy_([self.views[i] for i in seg["idx"]], src)
+                self._reduce(seg["flat"])
+            if self._comm is None:
+                pack_and_reduce()
+                return
+            self._comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm):
+                pack_and_reduce()
+        return hook
+
+    def finish_overlap(self):
+        if self._comm is not None:
+            torch.cuda.current_stream().wait_stream(self._comm)
+        for seg in self._segments:
+            seg["count"] = 0
+        self.attach()
+
+    def disable_overlap(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks, self._segments = [], None
+
+    def _reduce(self, flat):
+        group = getattr(self, "_group", None)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+                flat.div_(dist.get_world_size(group))
 
     def all_reduce_mean(self, group=None):
         """Mean over ranks (gradient of the global-batch mean loss): NCCL averages inside the collective, other

@@ -21,7 +21,8 @@ class GraphedTrainStep:
 
     def __init__(self, step_fn: Callable[[torch.Tensor], torch.Tensor], example: torch.Tensor,
                  zero_grad: Callable[[], None], optimizer: Optional[torch.optim.Optimizer] = None,
-                 warmup: int = 3, post_backward: Optional[Callable[[], None]] = None):
+                 warmup: int = 3, post_backward: Optional[Callable[[], None]] = None,
+                 capture_error_mode: Optional[str] = None):
         self.static_x = torch.empty_like(example, device="cuda")
         self.static_x.copy_(example)
         self.optimizer = optimizer
@@ -39,7 +40,12 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        if capture_error_mode is None:
+            # a process group's watchdog thread issues CUDA calls of its own: with NCCL collectives inside the capture
+            # only this thread's calls may invalidate it
+            import torch.distributed as dist
+            capture_error_mode = "thread_local" if dist.is_available() and dist.is_initialized() else "global"
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             zero_grad()
             self.static_loss = step_fn(self.static_x)
             self.static_loss.backward()

@@ -29,12 +29,14 @@ def _make_model():
     return torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 3))
 
 
-def _worker(rank, world, port, q, accumulate=True):
+def _worker(rank, world, port, q, accumulate=True, overlap=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     model = _make_model()
     bucket = dmod.FlatGradBucket(model.parameters(), accumulate=accumulate)
+    if overlap:      # one collective per Linear layer, issued from post-accumulate hooks during backward
+        bucket.enable_overlap([list(model[0].parameters()), list(model[2].parameters())])
     g = torch.Generator().manual_seed(1)
     x = torch.randn(10, 12, generator=g)
     y = torch.randn(10, 3, generator=g)
@@ -43,11 +45,16 @@ def _worker(rank, world, port, q, accumulate=True):
     # local mean over the shard, weighted so that the average over ranks is the global mean
     loss = ((model(x[lo:hi]) - y[lo:hi]) ** 2).sum() / (10 / world)
     loss.backward()
-    if not accumulate:
-        assert all(p.grad.data_ptr() != v.data_ptr() for p, v in zip(bucket.params, bucket.views))
-        bucket.pack()           # one multi-tensor copy; .grad now views the flat buffer
+    if overlap:
+        bucket.finish_overlap()
+        flat = bucket.flat.clone()
+    else:
+        if not accumulate:
+            assert all(p.grad.data_ptr() != v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+            bucket.pack()           # one multi-tensor copy; .grad now views the flat buffer
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+        flat = bucket.all_reduce_mean().clone()
     assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
-    flat = bucket.all_reduce_mean().clone()
     if rank == 0:
         q.put(flat)
     dist.barrier()
@@ -65,14 +72,14 @@ def test_shard_batch_covers_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-@pytest.mark.parametrize("accumulate", [True, False])
-def test_flat_bucket_allreduce_matches_full_batch(accumulate):
-    """world_size 2 over gloo: both bucket modes (gradients accumulated into the flat buffer / packed after backward)
-    reproduce the single-process full-batch gradient."""
+@pytest.mark.parametrize("accumulate,overlap", [(True, False), (False, False), (False, True)])
+def test_flat_bucket_allreduce_matches_full_batch(accumulate, overlap):
+    """world_size 2 over gloo: the bucket modes (gradients accumulated into the flat buffer / packed after backward /
+    packed and all-reduced per segment from backward hooks) reproduce the single-process full-batch gradient."""
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, accumulate)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, accumulate, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     flat = q.get()
