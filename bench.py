@@ -93,7 +93,7 @@ def oracle_step_fn(batch, frames):
     return step
 
 
-def run_cpu_baseline(frames, sample_batch=8, reps=2):
+def run_cpu_baseline(frames, sample_batch=64, reps=2):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     step = oracle_step_fn(sample_batch, frames)
@@ -106,8 +106,8 @@ def run_cpu_baseline(frames, sample_batch=8, reps=2):
     return {
         "value": sample_batch * frames / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
         "sample": f"oracle/bimamba_oracle.py (port of mamba_block.py + PN_BiMambas_Encoder), fp32, batch {sample_batch} "
-                  f"of the workload's batch, {frames} frames, {N_LAYERS} layers, fwd+bwd, best of {reps} after 1 warm-up "
-                  f"({best:.2f} s per sample step)",
+                  f"(the workload's own batch), {frames} frames, {N_LAYERS} layers, fwd+bwd (no optimizer step), best of {reps} "
+                  f"after 1 warm-up ({best:.2f} s per step)",
     }
 
 
@@ -116,19 +116,18 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_batch = 8
+    sample_batch = args.batch                     # the benchmarked batch itself (config 2: 64), not a sub-sample
     step = oracle_step_fn(sample_batch, args.frames)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
-    steps = max(1, min(args.steps, 8))            # bounded: each sample step is ~1-2 s of CPU work
+    steps = max(1, min(args.steps, 30))           # each step is ~2-4 s of CPU work on 8-16 threads
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
     value = sample_batch * args.frames * steps / dt
     sample = (f"oracle port of the reference's CPU path (the reference is Python and /root/reference is absent on the GPU "
-              f"box), fp32, batch {sample_batch} sample of batch {args.batch}, {args.frames} frames, fwd+bwd, "
-              f"{steps} timed steps")
+              f"box), fp32, batch {sample_batch} (the workload's batch), {args.frames} frames, fwd+bwd, {steps} timed steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * dt / steps,
@@ -243,23 +242,27 @@ def scan_bytes(frames, ndir, esize, backward):
 
 
 def scan_sweep(bm, peak):
-    """Config-5 points: single-direction selective_scan op, 524 288 frames, D=288, N=16."""
+    """Config 5 (BASELINE.json configs[4]): the single-direction selective_scan op on 524 288 frames, D = 288, N = 16,
+    every L in 64..8192, bf16 and fp32 I/O.  Three rows per point: `scan_fwd_infer` (torch.no_grad: nothing saved for a
+    backward - the bytes the op-boundary figure describes), `scan_fwd` (training forward: also writes the fp32
+    checkpoints every 8 steps and ypre) and `scan_bwd`; all against SURVEY 8(d)'s algorithmic bytes."""
     out = []
     g = torch.Generator(device="cuda").manual_seed(0)
-    for dtype, name, Ls in ((torch.bfloat16, "bf16", (64, 256, 1024, 4096, 8192)), (torch.float32, "f32", (256, 2048))):
-        for L in Ls:
+    for dtype, name in ((torch.bfloat16, "bf16"), (torch.float32, "f32")):
+        for L in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
             Bsz = (1 << 19) // L
-            u = torch.randn(Bsz, D_INNER, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
-            delta = (0.5 * torch.randn(Bsz, D_INNER, L, device="cuda", generator=g)).to(dtype).requires_grad_(True)
-            z = torch.randn(Bsz, D_INNER, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
-            Bm = torch.randn(Bsz, D_STATE, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
-            Cm = torch.randn(Bsz, D_STATE, L, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            mk = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+            u = mk(Bsz, D_INNER, L).to(dtype).requires_grad_(True)
+            delta = (0.5 * mk(Bsz, D_INNER, L)).to(dtype).requires_grad_(True)
+            z = mk(Bsz, D_INNER, L).to(dtype).requires_grad_(True)
+            Bm = mk(Bsz, D_STATE, L).to(dtype).requires_grad_(True)
+            Cm = mk(Bsz, D_STATE, L).to(dtype).requires_grad_(True)
             A = (-torch.exp(torch.log(torch.arange(1, D_STATE + 1, device="cuda", dtype=torch.float32)).repeat(D_INNER, 1)
-                            + 0.1 * torch.randn(D_INNER, D_STATE, device="cuda", generator=g))).requires_grad_(True)
-            Dp = (1 + 0.1 * torch.randn(D_INNER, device="cuda", generator=g)).requires_grad_(True)
+                            + 0.1 * mk(D_INNER, D_STATE))).requires_grad_(True)
+            Dp = (1 + 0.1 * mk(D_INNER)).requires_grad_(True)
             dt0 = torch.exp(torch.rand(D_INNER, device="cuda", generator=g) * (math.log(0.1) - math.log(1e-3)) + math.log(1e-3))
             bias = (dt0 + torch.log(-torch.expm1(-dt0))).requires_grad_(True)     # mamba dt-bias init range
-            cot = torch.randn(Bsz, D_INNER, L, device="cuda", generator=g).to(dtype)
+            cot = mk(Bsz, D_INNER, L).to(dtype)
             timer = EventTimer()
             bm._lib.kernel_timer = timer
             for it in range(5):
@@ -267,10 +270,16 @@ def scan_sweep(bm, peak):
                 o.backward(cot)
                 for t in (u, delta, z, Bm, Cm, A, Dp, bias):
                     t.grad = None
-            bm._lib.kernel_timer = None
             times = timer.summary()
+            timer = EventTimer()
+            bm._lib.kernel_timer = timer
+            with torch.no_grad():
+                for it in range(5):
+                    o = bm.selective_scan_fn(u, delta, A, Bm, Cm, Dp, z, bias, True)
+            bm._lib.kernel_timer = None
+            times["scan_fwd_infer"] = timer.summary()["scan_fwd"]
             es = 4 if dtype == torch.float32 else 2
-            for kname, bwd in (("scan_fwd", False), ("scan_bwd", True)):
+            for kname, bwd in (("scan_fwd_infer", False), ("scan_fwd", False), ("scan_bwd", True)):
                 ms = statistics.median(times[kname][2:])
                 gbs = scan_bytes(Bsz * L, 1, es, bwd) / (ms * 1e-3) / 1e9
                 out.append({"kernel": kname, "io": name, "L": L, "batch": Bsz, "ms": round(ms, 4),
@@ -278,6 +287,39 @@ def scan_sweep(bm, peak):
             del u, delta, z, Bm, Cm, cot, o
             torch.cuda.empty_cache()
     return out
+
+
+def gemm_roofline(bm, B, L, flush):
+    """The in_proj GEMM of the block at the benchmark shape (M = B*L, K = 144, N = 576, bf16, fp32 accumulate) timed
+    alone (CUDA events around each launch, L2 flushed before each): flops / t against the measured dense bf16 peak and
+    bytes / t against the measured HBM peak."""
+    M, K, N = B * L, D_MODEL, 2 * D_INNER
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    ts = []
+    for it in range(12):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        bm.ops.gemm_nt(a, w)
+        e.record()
+        ts.append((s, e))
+    torch.cuda.synchronize()
+    ms = statistics.median([s.elapsed_time(e) for s, e in ts[2:]])
+    flops = 2.0 * M * K * N
+    nbytes = 2.0 * (M * K + N * K + M * N)
+    tf_peak, tf_src = 1642.8, "fallback"
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            tf_peak, tf_src = json.load(f).get("bf16_tflops", tf_peak), "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)"
+    hbm_peak, _ = load_peaks()
+    return {"kernel": "gemm_nt_kernel<bf16> in_proj (M %d, K %d, N %d), tcgen05 + TMEM + TMA" % (M, K, N), "bound": "tensor",
+            "achieved": flops / (ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / tf_peak,
+            "peak_source": tf_src, "avg_launch_ms": ms, "flops_per_launch": flops, "algorithmic_bytes_per_launch": nbytes,
+            "hbm_achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+            "note": "arithmetic intensity %.0f flop/B is below the B200 ridge (~250): stand-alone the product is bound by memory "
+                    "and launch latency, not by the tensor pipe (DESIGN.md 4.5)" % (flops / nbytes)}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -471,17 +513,25 @@ def run_ours(args, rank, world, local_rank):
                     % (fwd_ms, scan_bytes(B * L, 2, 2, False) / (fwd_ms * 1e-3) / 1e9),
             "kernels_ms": {k: round(statistics.mean(v[len(v) // 3:]), 4) for k, v in times.items()},
         }
+        fwd_alg = scan_bytes(B * L, 2, 2, False)
+        roofline_more = [
+            {"kernel": "scan_fwd_warp_kernel<bf16> (training forward, both directions, one launch per layer)", "bound": "hbm",
+             "achieved": fwd_alg / (fwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+             "frac": fwd_alg / (fwd_ms * 1e-3) / 1e9 / peak, "avg_launch_ms": fwd_ms, "algorithmic_bytes_per_launch": fwd_alg,
+             "traffic": None, "note": "(4D+2N)*2 B per frame per direction (SURVEY 8d); MUFU-bound: 16 ex2 per element (DESIGN.md 4.1)"},
+            gemm_roofline(bm, B, L, flush),
+        ]
         sweep = None if args.no_sweep else scan_sweep(bm, peak)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = run_cpu_baseline(L)
+            cpu = run_cpu_baseline(L, sample_batch=B)
         line = {
             "metric": METRIC, "value": frames_total / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args, world), l2="flushed between steps (256 MB write, untimed); per-step CUDA events summed",
                            launch="CUDA-graph replay" if use_graph else "eager", state="fp32", weights="fp32 master, bf16 autocast",
-                           gemm="tcgen05 (this repo)" if bm.ops.TC_GEMM else "cuBLAS",
+                           gemm="tcgen05 (this repo)",
                            comm=(None if world == 1 else {"overlap": "NCCL all-reduce (AVG) per encoder layer inside the step "
                                  "graph, overlapping the remaining backward", "graph": "one NCCL all-reduce inside the step graph",
                                  "eager": "one NCCL all-reduce after the graph"}[args.comm]),
@@ -495,6 +545,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline,
+            "roofline_more": roofline_more,
             "cpu_baseline": cpu,
             "scan_sweep": sweep,
             "loss": loss_val,

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 4
+#define BIMAMBA_ABI_VERSION 5
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -116,6 +116,23 @@ typedef struct bimamba_scan_desc {
 
 int bimamba_abi_version(void);
 const char* bimamba_last_error(void);
+
+/* Tuning knobs: force a kernel variant (parity tests of every shipped variant, tuning experiments).  0 = automatic.
+ * Process-wide; not meant to change while launches are in flight on other threads. */
+#define BIMAMBA_TUNE_SCAN_FWD 0     /* 1 = wide CTAs sharing the staged rows, 3 = one warp per CTA                 */
+#define BIMAMBA_TUNE_CONV_BWD 1     /* 1 = shared-memory tile kernel instead of the register-window kernel         */
+#define BIMAMBA_TUNE_GEMM_KERNEL 2  /* 1 = one tile per CTA, 2 = persistent warp-specialised                       */
+#define BIMAMBA_TUNE_GEMM_BN 3      /* tile width override                                                         */
+#define BIMAMBA_TUNE_GEMM_STAGES 4  /* TMA ring depth override                                                     */
+#define BIMAMBA_TUNE_COUNT 5
+int bimamba_set_tuning(int knob, int value);
+int bimamba_get_tuning(int knob);
+
+/* Bytes of the caller-allocated workspaces of the scan calls (for hosts that do not re-derive the geometry):
+ * forward with want_ckpt != 0: ckpt (fp32, (batch, ndir, nckpt, dim, 16), only when nckpt > 1) followed by ypre
+ * ((batch, ndir, seqlen, dim) in io_dtype); backward: dbc_part + dA_part + dD_part + dbias_part (all fp32). */
+size_t bimamba_scan_fwd_workspace_bytes(int batch, int ndir, int seqlen, int dim, int io_dtype, int want_ckpt);
+size_t bimamba_scan_bwd_workspace_bytes(int batch, int ndir, int seqlen, int dim);
 
 /* Chooses the channel-group width for (seqlen, dim, batch*ndir); backward != 0 selects the
  * backward kernel's geometry.  Returns nckpt = ceil(seqlen / 8), the number of checkpoints per

@@ -15,7 +15,7 @@ F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
 FLAG_DTR_PADDED = 2
 FLAG_SILU = 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 CHUNK = 16
 
 EXPORTS = (
@@ -24,7 +24,8 @@ EXPORTS = (
     "bimamba_causal_conv1d_fwd", "bimamba_causal_conv1d_bwd", "bimamba_conv_bwd_slices",
     "bimamba_reduce_partials", "bimamba_layernorm_fwd", "bimamba_layernorm_bwd_blocks", "bimamba_layernorm_bwd",
     "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_gemm_tn_splits", "bimamba_gemm_tn", "bimamba_adamw_chunk", "bimamba_adamw_step", "bimamba_head_fwd", "bimamba_colsum_slices", "bimamba_colsum", "bimamba_pack_weights", "bimamba_cast_transpose",
-    "bimamba_gelu_fwd", "bimamba_gelu_bwd", "bimamba_reduce_rows32", "bimamba_finalize_param_grads", "bimamba_head_pool_bwd",
+    "bimamba_gelu_fwd", "bimamba_gelu_bwd", "bimamba_reduce_rows32", "bimamba_finalize_param_grads", "bimamba_head_pool_bwd", "bimamba_set_tuning", "bimamba_get_tuning",
+    "bimamba_scan_fwd_workspace_bytes", "bimamba_scan_bwd_workspace_bytes",
 )
 
 
@@ -131,6 +132,14 @@ def load() -> C.CDLL:
         lib.bimamba_finalize_param_grads.argtypes = [vp] * 12 + [i32] * 6 + [vp]
         lib.bimamba_head_pool_bwd.restype = i32
         lib.bimamba_head_pool_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_float, i32, vp]
+        lib.bimamba_set_tuning.restype = i32
+        lib.bimamba_set_tuning.argtypes = [i32, i32]
+        lib.bimamba_get_tuning.restype = i32
+        lib.bimamba_get_tuning.argtypes = [i32]
+        lib.bimamba_scan_fwd_workspace_bytes.restype = C.c_size_t
+        lib.bimamba_scan_fwd_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+        lib.bimamba_scan_bwd_workspace_bytes.restype = C.c_size_t
+        lib.bimamba_scan_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32]
         got = lib.bimamba_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError(f"libbimamba ABI {got} != expected {ABI_VERSION}; rebuild the library")
@@ -151,7 +160,26 @@ def scan_plan(seqlen: int, dim: int, rows: int, backward: bool = False):
     gc, ng = C.c_int(0), C.c_int(0)
     n = load().bimamba_scan_plan(int(seqlen), int(dim), int(rows), int(backward), C.byref(gc), C.byref(ng))
     g = gc.value
-    ov = os.environ.get("BIMAMBA_BWD_G" if backward else "BIMAMBA_FWD_G")   # tuning experiments only
-    if ov:
-        g = int(ov)
     return g, (dim + g - 1) // g, n
+
+
+TUNE_SCAN_FWD, TUNE_CONV_BWD, TUNE_GEMM_KERNEL, TUNE_GEMM_BN, TUNE_GEMM_STAGES = range(5)
+
+
+class tuning:
+    """Context manager that forces a kernel variant (parity tests of every shipped variant, tuning experiments):
+    `with tuning(TUNE_SCAN_FWD, 1): ...`.  0 = automatic choice."""
+
+    def __init__(self, knob: int, value: int):
+        self.knob, self.value = knob, value
+
+    def __enter__(self):
+        lib = load()
+        self.old = lib.bimamba_get_tuning(self.knob)
+        if lib.bimamba_set_tuning(self.knob, self.value) != 0:
+            raise RuntimeError("bimamba_set_tuning: unknown knob")
+        return self
+
+    def __exit__(self, *a):
+        load().bimamba_set_tuning(self.knob, self.old)
+        return False

@@ -10,6 +10,10 @@ void set_err(const char* msg) {
   g_err[i] = 0;
 }
 
+// Tuning knobs (tests and tuning experiments force kernel variants through bimamba_set_tuning; launches read these
+// process-wide integers - no getenv on any launch path).  0 = automatic choice.
+int g_tune[BIMAMBA_TUNE_COUNT] = {0, 0, 0, 0, 0};
+
 int check_desc(const bimamba_scan_desc* d, bool bwd) {
   if (!d) { set_err("null descriptor"); return -1; }
   if (d->dstate != kN) { set_err("dstate must be 16"); return -2; }
@@ -36,6 +40,34 @@ using namespace bimamba;
 
 extern "C" int bimamba_abi_version(void) { return BIMAMBA_ABI_VERSION; }
 extern "C" const char* bimamba_last_error(void) { return g_err; }
+
+extern "C" int bimamba_set_tuning(int knob, int value) {
+  if (knob < 0 || knob >= BIMAMBA_TUNE_COUNT) { set_err("set_tuning: unknown knob"); return -1; }
+  g_tune[knob] = value;
+  return 0;
+}
+
+extern "C" int bimamba_get_tuning(int knob) { return (knob < 0 || knob >= BIMAMBA_TUNE_COUNT) ? 0 : g_tune[knob]; }
+
+/* Workspace sizes a non-Python host needs to allocate before the backward calls: the partial-sum buffers
+ * of bimamba_selective_scan_bwd and the checkpoint / ypre tensors of bimamba_selective_scan_fwd, in BYTES. */
+extern "C" size_t bimamba_scan_fwd_workspace_bytes(int batch, int ndir, int seqlen, int dim, int io_dtype, int want_ckpt) {
+  if (batch <= 0 || ndir <= 0 || seqlen <= 0 || dim <= 0 || !want_ckpt) return 0;
+  const size_t nck = (size_t)(seqlen + BIMAMBA_CKPT - 1) / BIMAMBA_CKPT;
+  const size_t es = io_dtype == BIMAMBA_F32 ? 4 : 2;
+  const size_t ckpt = nck > 1 ? (size_t)batch * ndir * nck * dim * kN * 4 : 0;
+  return ckpt + (size_t)batch * ndir * seqlen * dim * es;       /* ckpt (fp32) followed by ypre (io dtype) */
+}
+
+extern "C" size_t bimamba_scan_bwd_workspace_bytes(int batch, int ndir, int seqlen, int dim) {
+  if (batch <= 0 || ndir <= 0 || seqlen <= 0 || dim <= 0) return 0;
+  int G = 0, ng = 0;
+  bimamba_scan_plan(seqlen, dim, batch * ndir, 1, &G, &ng);
+  const size_t dbc = (size_t)batch * ng * seqlen * ndir * 2 * kN * 4;
+  const size_t dA = (size_t)batch * ndir * dim * kN * 4;
+  const size_t dDb = (size_t)batch * ndir * dim * 4;
+  return dbc + dA + 2 * dDb;                                     /* dbc_part, dA_part, dD_part, dbias_part */
+}
 
 extern "C" int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, int* group_channels, int* ngroups) {
   int G;

@@ -17,6 +17,7 @@ constexpr int kN = BIMAMBA_DSTATE;  // d_state handled by these kernels
 constexpr int kXW = 48;             // staged row of projection features: B(16) | C(16) | dt_r(<=16)
 
 void set_err(const char* msg);  // api.cu
+extern int g_tune[BIMAMBA_TUNE_COUNT];  // api.cu: bimamba_set_tuning
 
 // ---- element conversion (arithmetic is always fp32; storage type is the template parameter)
 __device__ __forceinline__ float to_f(float v) { return v; }

@@ -553,7 +553,7 @@ extern "C" int bimamba_causal_conv1d_bwd(const void* x, const float* weight, con
   const int vec = (dim % ev == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(dout) % 16 == 0) &&
                   (x_bs % ev == 0) && (x_ts % ev == 0) && (dout_bs % ev == 0) && (dout_ds % ev == 0) && (dout_ts % ev == 0);
   // register-window kernel: K = 4 and every row addressable as 4-channel vectors
-  const bool seg4 = width == 4 && getenv("BIMAMBA_CONV_BWD_TILE") == nullptr &&
+  const bool seg4 = width == 4 && g_tune[BIMAMBA_TUNE_CONV_BWD] != 1 &&
                     vec4_ok(dtype, dim, {x, dout, dx, dz_in, dz_out}, {x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts});
   if (seg4) {
     const int64_t total = (int64_t)batch * conv_bwd_time_tiles(seqlen) * (dim / 4);

@@ -651,7 +651,7 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
   int block_n = bimamba_gemm_nt_block_n_k(N, K);
   int max_stages = kGStagesMax;
   // persistent warp-specialised variant when there is more than one tile per SM (and rows are 16-byte friendly)
-  const char* kv = getenv("BIMAMBA_GEMM_KERNEL");   // tuning experiments only: "tile" | "persist"
+  const int kv = g_tune[BIMAMBA_TUNE_GEMM_KERNEL];   // tuning experiments / variant tests only: 1 = tile, 2 = persistent
   const int osz = out_dtype == BIMAMBA_F32 ? 4 : 2;
   const bool can_stage = (N % (16 / osz) == 0) && (ldc % (16 / osz) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                          (!addend || (reinterpret_cast<uintptr_t>(addend) & 15) == 0);
@@ -660,11 +660,11 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
     const int bnp = persist_block_n(N);
     const int64_t nt = ((M + kGM - 1) / kGM) * ((N + bnp - 1) / bnp);
     persist = can_stage && nt >= 4 * 148;   // measured: below ~4 tiles per SM the one-tile-per-CTA kernel wins
-    if (kv) persist = can_stage && kv[0] == 'p';
+    if (kv) persist = can_stage && kv == 2;
     if (persist) block_n = bnp;
   }
-  if (const char* ov = getenv("BIMAMBA_GEMM_BN")) block_n = atoi(ov);        // tuning experiments only
-  if (const char* ov = getenv("BIMAMBA_GEMM_STAGES")) max_stages = atoi(ov);  // tuning experiments only
+  if (g_tune[BIMAMBA_TUNE_GEMM_BN]) block_n = g_tune[BIMAMBA_TUNE_GEMM_BN];            // tuning experiments only
+  if (g_tune[BIMAMBA_TUNE_GEMM_STAGES]) max_stages = g_tune[BIMAMBA_TUNE_GEMM_STAGES];  // tuning experiments only
   CUtensorMap map_a, map_b;
   int rc = make_map(&map_a, A, in_dtype, M, K, lda, kGM);
   if (rc) return rc;
@@ -693,8 +693,9 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
     uint32_t pcols = 32;
     while (pcols < 2 * acc_stride) pcols <<= 1;
     const size_t psmem = (size_t)kPStages * stage_bytes + tile_bytes + 1024;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev);
     const unsigned pgrid = (unsigned)(ntiles < sms ? ntiles : sms);
 #define GEMM_PLAUNCH(TOUT)                                                                                         \
   do {                                                                                                             \
@@ -787,11 +788,8 @@ extern "C" int bimamba_gemm_tn(const void* A, int64_t lda, const void* B, int64_
                          ((uint32_t)(pl.block_q >> 3) << 17) | ((uint32_t)(kGM >> 4) << 24);
   dim3 grid((unsigned)((pl.NP + kGM - 1) / kGM), (unsigned)((pl.NQ + pl.block_q - 1) / pl.block_q), (unsigned)pl.nsplit);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 6 * kTNBox + 1024);
-    attr_set = true;
-  }
+  // per device / context attribute: set on every launch (a process-wide flag would miss the second device)
+  cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 6 * kTNBox + 1024);
   gemm_tn_kernel<<<grid, kGThreads, smem, st>>>(map_p, map_q, part, (int)M, pl.NP, pl.NQ, pl.block_q, pl.per, idesc, tmem_cols);
   tn_reduce_kernel<<<(unsigned)(((int64_t)N1 * N2 + 255) / 256), 256, 0, st>>>(part, C, pl.nsplit, pl.NP, pl.NQ, pl.p_is_a);
   cudaError_t e = cudaGetLastError();

@@ -1,7 +1,6 @@
-// Selective scan, backward, ONE LANE PER CHANNEL variant (both time directions in one launch).  sm_100a.
+// Selective scan, backward, ONE LANE PER CHANNEL (both time directions in one launch).  sm_100a.
 //
-// Same gradients and the same descriptor / outputs as scan_bwd.cu (autograd of
-// src/models/modules/mamba_block.py:80-120, :61):
+// Gradients (autograd of src/models/modules/mamba_block.py:80-120, :61):
 //   g = dout * silu(z);  dz = dout * ypre * silu'(z)
 //   dh[t] = g[t] C[t] + a[t+1] dh[t+1]                       (reverse-time recurrence)
 //   ddelta[t] = sum_n dh a h[t-1] A + u sum_n dh B;  du[t] = g D + delta sum_n dh B
@@ -14,8 +13,9 @@
 //     re-run forward from its checkpoint and the seven intermediate states h[0..6] are KEPT IN REGISTERS (7 x 16):
 //     with every loop unrolled the kernel uses all 255 registers, i.e. 8 warps per SM - which is all the Phase-6
 //     shapes offer anyway (batch 64 x 2 directions x 288 channels = 7.8 warps per SM) - and needs no (L, D, N)
-//     tensor, no shared-memory history and less than half the instructions of the state-pair kernel (404 vs 886 per
-//     element).  Keeping part of the history in shared memory was measured slower.
+//     tensor, no shared-memory history and less than half the instructions of round 1's state-pair kernel (404 vs 886
+//     per element; that kernel was removed in round 2).  Keeping part of the history in shared memory was measured
+//     slower; so was giving a channel to four lanes with 4 states each (profiles/r2_history.md).
 //   * the decay a[t] = exp2(delta A) is recomputed in the reverse pass (MUFU is not the limiter here: 36 per element,
 //     XU pipe 29 %).
 //   * dB / dC need a sum over channels: per step every lane writes its 32 products to a padded row of shared memory
@@ -29,10 +29,8 @@
 //     that are not 16-byte friendly).
 //   * all element math is branch-free (the softplus / gate / ypre flags select), and the eight delta chains of a
 //     chunk are computed before the recurrence, so the unrolled steps interleave.
-//   * kSplit = 2 gives a channel to two neighbouring lanes with 8 states each (128 registers, twice the warps); it is
-//     covered by the parity tests but measured slower, so the dispatch never picks it (BIMAMBA_BWD_LANES=2 forces it).
-#include <cstdlib>
-
+//   * the template also describes kSplit = 2 (two neighbouring lanes with 8 states each) and kNW > 1 (wider CTAs):
+//     both were measured slower in round 1 and are no longer instantiated.
 #include "common.cuh"
 
 namespace bimamba {
@@ -464,16 +462,11 @@ static void launch_lane3(const bimamba_scan_desc* d, cudaStream_t st) {
   scan_bwd_lane_kernel<T, kMode, kNW, kSplit><<<grid, 32 * kNW, smem, st>>>(*d);
 }
 
-// group_channels == 32 (checked by the caller).
+// group_channels == 32 (checked by the caller).  One warp per CTA, one lane per channel: the two-lanes-per-channel
+// instantiation (kSplit = 2) and wider CTAs (kNW > 1) were measured slower at every size (round 1) and are not built.
 template <typename T, int kMode>
 static void launch_lane2(const bimamba_scan_desc* d, cudaStream_t st) {
-  const int64_t lanes = (int64_t)d->batch * d->ndir * d->dim;
-  const char* force = getenv("BIMAMBA_BWD_LANES");   // tuning experiments and the parity tests of both variants
-  (void)lanes;   // measured: one lane per channel wins at both ends (0.23 vs 0.27 ms at batch 64 x 201 frames, 3.6 vs 3.8 ms
-                 // at 2048 x 256); the two-lane variant stays selectable for experiments and is covered by the tests
-  const bool split = force ? atoi(force) == 2 : false;
-  if (split) launch_lane3<T, kMode, 2, 2>(d, st);
-  else launch_lane3<T, kMode, 1, 1>(d, st);
+  launch_lane3<T, kMode, 1, 1>(d, st);
 }
 
 template <typename T>
@@ -492,4 +485,19 @@ void launch_bwd_lane(const bimamba_scan_desc* d, cudaStream_t st) {
   }
 }
 
+int check_desc(const bimamba_scan_desc* d, bool bwd);  // api.cu
+
 }  // namespace bimamba
+
+using namespace bimamba;
+
+extern "C" int bimamba_selective_scan_bwd(const bimamba_scan_desc* d, bimamba_stream_t stream) {
+  if (d && (d->batch == 0 || d->seqlen == 0)) return 0;
+  int rc = check_desc(d, true);
+  if (rc) return rc;
+  if (d->group_channels != 32) { set_err("backward group_channels must be 32 (use bimamba_scan_plan)"); return -5; }
+  launch_bwd_lane(d, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}

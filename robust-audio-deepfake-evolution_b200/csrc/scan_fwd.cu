@@ -20,12 +20,11 @@
 //   * direction 1 walks the same storage back to front (t = L-1-step): flip(M(flip(x))) of
 //     src/models/DualStreamSEMamba.py:476-478 with no flipped copy; both directions are
 //     blockIdx.y of the same launch.
-//   * small problems (fewer than ~16 warps per SM of channel lanes) use the two-lanes-per-channel variant in
-//     scan_fwd2.cu: same math, twice the warps.
+//   * small problems (fewer than ~16 warps per SM of channel lanes) and fp32 I/O use the one-warp-per-CTA kernel in
+//     scan_fwd1.cu: same math, no block barrier.
 //   * training forward also writes the fp32 state entering every 8-step chunk ("checkpoints",
 //     (B, dir, chunk, D, 16): 64 contiguous bytes per thread) and the pre-gate y; the backward
 //     recomputes the states of a chunk from its checkpoint (no (B, L, D, N) tensor).
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -224,7 +223,6 @@ static void launch_fwd(const bimamba_scan_desc* d, cudaStream_t st) {
 }
 
 int check_desc(const bimamba_scan_desc* d, bool bwd);  // api.cu
-void launch_fwd_pair(const bimamba_scan_desc* d, cudaStream_t st);  // scan_fwd2.cu
 void launch_fwd_warp(const bimamba_scan_desc* d, cudaStream_t st);  // scan_fwd1.cu
 
 }  // namespace bimamba
@@ -238,18 +236,17 @@ extern "C" int bimamba_selective_scan_fwd(const bimamba_scan_desc* d, bimamba_st
   const int G = d->group_channels;
   if (G < 32 || G > kFwdMaxThreads || (G & 31)) { set_err("forward group_channels must be 32, 64, 96 or 128 (use bimamba_scan_plan)"); return -5; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // Three kernels, same math (forced in turn by tests/test_gpu_ops.py::test_scan_forward_variants):
+  // Two kernels, same math (forced in turn by tests/test_gpu_ops.py::test_scan_forward_variants through
+  // bimamba_set_tuning(BIMAMBA_TUNE_SCAN_FWD, .)):
   //   3: one lane per channel, one warp per CTA (scan_fwd1.cu) - the Phase-6 sizes (fewer than ~16 warps per SM of
-  //      channel lanes: 0.074 ms per launch at batch 64 x 201 frames, 0.099 for variant 2, 0.115 for variant 1) and fp32 I/O
-  //      (1.04 vs 1.28 ms at 2048 x 256);
-  //   1: one lane per channel, wide CTAs sharing the staged rows - large 16-bit problems (1.06 vs 1.09 ms);
-  //   2: two lanes per channel (scan_fwd2.cu) - kept for experiments.
+  //      channel lanes: 0.074 ms per launch at batch 64 x 201 frames vs 0.115 for variant 1) and fp32 I/O (1.04 vs 1.28 ms
+  //      at 2048 x 256);
+  //   1: one lane per channel, wide CTAs sharing the staged rows - large 16-bit problems (1.06 vs 1.09 ms).
+  // (A third, two-lanes-per-channel kernel lost to both at every size and was removed in round 2.)
   const int64_t lanes = (int64_t)d->batch * d->ndir * d->dim;
-  const char* force = getenv("BIMAMBA_FWD_LANES");   // tuning experiments and the variant tests
-  const int variant = force ? atoi(force) : ((lanes < (int64_t)148 * 16 * 32 || d->io_dtype == BIMAMBA_F32) ? 3 : 1);
-  if (variant == 2) {
-    launch_fwd_pair(d, st);
-  } else if (variant == 3) {
+  const int force = g_tune[BIMAMBA_TUNE_SCAN_FWD];
+  const int variant = force ? force : ((lanes < (int64_t)148 * 16 * 32 || d->io_dtype == BIMAMBA_F32) ? 3 : 1);
+  if (variant == 3) {
     launch_fwd_warp(d, st);
   } else {
     switch (d->io_dtype) {

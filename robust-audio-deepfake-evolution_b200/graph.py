@@ -5,9 +5,31 @@ launch-latency bound; capturing it once and replaying removes 
 loop.  This plays the role a tracing compiler would: explicit capture, static buffers."""
 from __future__ import annotations
 
+import copy
 from typing import Callable, Optional
 
 import torch
+
+
+def _snapshot(optimizer):
+    params = [p for g in optimizer.param_groups for p in g["params"]]
+    return params, [p.detach().clone() for p in params], copy.deepcopy(optimizer.state_dict())
+
+
+def _restore(optimizer, snap):
+    """Undo the warm-up's optimizer steps: parameters back to their values, optimizer state back to what it was (or,
+    if there was none yet, to the freshly initialised value: zero moments, step 0)."""
+    params, values, sd = snap
+    with torch.no_grad():
+        for p, v in zip(params, values):
+            p.copy_(v)
+    if sd["state"] or hasattr(optimizer, "_export_state"):      # FusedAdamW also resets itself from an empty state
+        optimizer.load_state_dict(sd)
+    else:
+        for st in optimizer.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
 
 
 class GraphedTrainStep:
@@ -17,15 +39,21 @@ class GraphedTrainStep:
 
     step_fn(x) must return a scalar loss tensor and must be capture-safe (no host sync).
     `run(x)` copies x (host-pinned or device) into the static input, replays, and returns the static
-    loss tensor (read it with .item() to synchronise)."""
+    loss tensor (read it with .item() to synchronise).
+
+    The `warmup` iterations before the capture run real optimizer steps on the example batch (lazy initialisation of
+    handles, function attributes and optimizer state must happen outside the capture); with restore_after_warmup
+    (default) the parameters and the optimizer state are put back afterwards, so building the runner - e.g. right
+    after loading a checkpoint - does not change the model, the moments, or the step count."""
 
     def __init__(self, step_fn: Callable[[torch.Tensor], torch.Tensor], example: torch.Tensor,
                  zero_grad: Callable[[], None], optimizer: Optional[torch.optim.Optimizer] = None,
                  warmup: int = 3, post_backward: Optional[Callable[[], None]] = None,
-                 capture_error_mode: Optional[str] = None):
+                 capture_error_mode: Optional[str] = None, restore_after_warmup: bool = True):
         self.static_x = torch.empty_like(example, device="cuda")
         self.static_x.copy_(example)
         self.optimizer = optimizer
+        snap = _snapshot(optimizer) if (optimizer is not None and restore_after_warmup) else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -39,6 +67,9 @@ class GraphedTrainStep:
                     optimizer.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if snap is not None:
+            _restore(optimizer, snap)
+            torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         if capture_error_mode is None:
             # a process group's watchdog thread issues CUDA calls of its own: with NCCL collectives inside the capture

@@ -427,11 +427,8 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
 # ----------------------------------------------------------------------------------------
 # projections: C = A . B^T on the tcgen05 tensor cores (mamba_block.py:48, :73, :62)
 # ----------------------------------------------------------------------------------------
-TC_GEMM = os.environ.get("BIMAMBA_GEMM", "tcgen05") != "cublas"   # cublas = library GEMMs (A/B comparison only)
-
-
 def _tc_ok(A: torch.Tensor, B: torch.Tensor) -> bool:
-    return (TC_GEMM and A.dtype in (torch.bfloat16, torch.float16) and B.dtype == A.dtype and A.dim() == 2
+    return (A.dtype in (torch.bfloat16, torch.float16) and B.dtype == A.dtype and A.dim() == 2
             and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1 and A.stride(0) % 8 == 0
             and B.stride(0) % 8 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and A.shape[0] > 0)
 
@@ -471,7 +468,7 @@ def gemm_nt(A, B, bias=None, addend=None, out_dtype=None, out=None):
 def gemm_tn(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     """A (M, N1)^T . B (M, N2) -> (N1, N2) fp32: the weight gradient dY^T X on the tcgen05 kernel (MN-major operands,
     deterministic split over the M rows).  fp32 / misaligned operands use the library product."""
-    if not (_tc_ok(A, B) and os.environ.get("BIMAMBA_WGRAD", "tcgen05") != "cublas"):
+    if not _tc_ok(A, B):
         return mm_f32(A.t(), B)
     lib = _lib.load()
     M, N1 = A.shape

@@ -65,6 +65,47 @@ class FusedAdamW(torch.optim.Optimizer):
         for group, g in zip(self.param_groups, self._groups):
             self._sync_hyper(group, g)
 
+    # ---- checkpoint / resume: torch.optim.AdamW's layout (state[p] = {step, exp_avg, exp_avg_sq}) ------------------
+    def _export_state(self):
+        """Refresh `self.state` so that `state_dict()` holds the live moments and the step counter."""
+        if self._groups is None:
+            return
+        for g in self._groups:
+            step = g["state"].detach().clone().reshape(())
+            for p, o in zip(g["params"], g["offs"]):
+                n = p.numel()
+                self.state[p] = {"step": step, "exp_avg": g["m"][o:o + n].view_as(p), "exp_avg_sq": g["v"][o:o + n].view_as(p)}
+
+    def state_dict(self):
+        self._export_state()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Loads a FusedAdamW or torch.optim.AdamW state_dict: moments are copied into the flat buffers the kernel
+        reads and the step counter is restored (bias correction continues where it stopped).  An empty state resets
+        the optimizer."""
+        if self._groups is None:
+            self._build()                                   # before the load: _build() re-points state at its own (zero) buffers
+        super().load_state_dict(state_dict)
+        for g in self._groups:
+            g["hyper_host"] = None                          # param_groups may carry new hyper-parameters
+            step = None
+            for p, o in zip(g["params"], g["offs"]):
+                n = p.numel()
+                st = self.state.get(p, None)
+                if st and "exp_avg" in st:
+                    g["m"][o:o + n].copy_(st["exp_avg"].reshape(-1).to(torch.float32))
+                    g["v"][o:o + n].copy_(st["exp_avg_sq"].reshape(-1).to(torch.float32))
+                    if "step" in st:
+                        step = float(st["step"]) if step is None else max(step, float(st["step"]))
+                else:
+                    g["m"][o:o + n].zero_()
+                    g["v"][o:o + n].zero_()
+            g["state"].fill_(0.0 if step is None else step)
+        for group, g in zip(self.param_groups, self._groups):
+            self._sync_hyper(group, g)
+        self._export_state()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -81,15 +122,18 @@ class FusedAdamW(torch.optim.Optimizer):
                 continue
             self._sync_hyper(group, g)
             for p in ps:
-                if p.grad is None:
-                    raise RuntimeError("FusedAdamW.step: a parameter has no gradient")
-                if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+                if p.grad is not None and (p.grad.dtype != torch.float32 or not p.grad.is_contiguous()):
                     p.grad = p.grad.to(torch.float32).contiguous()
-            gptrs = tuple(p.grad.data_ptr() for p in ps)
+            # parameters without a gradient are skipped, as torch.optim.AdamW does (src/main.py:453 hands the optimizer
+            # the whole model, including tensors that never receive one): their table entry has n = 0
+            gptrs = tuple(0 if p.grad is None else p.grad.data_ptr() for p in ps)
+            if not any(gptrs):
+                continue
             if gptrs != g["gptrs"]:       # gradients moved (first step, or freshly allocated by autograd)
                 tab = np.empty((len(ps), 5), dtype=np.int64)
                 for i, (p, o) in enumerate(zip(ps, g["offs"])):
-                    tab[i] = (p.data_ptr(), gptrs[i], g["m"].data_ptr() + 4 * int(o), g["v"].data_ptr() + 4 * int(o), p.numel())
+                    tab[i] = (p.data_ptr(), gptrs[i], g["m"].data_ptr() + 4 * int(o), g["v"].data_ptr() + 4 * int(o),
+                              p.numel() if gptrs[i] else 0)
                 host = torch.from_numpy(tab.reshape(-1)).pin_memory()
                 if torch.cuda.is_current_stream_capturing():
                     self._keep_captured.append(host)

@@ -114,3 +114,29 @@ def test_python_surface_mirrors_reference_and_has_no_cpu_fallback():
     pkg = bm.install_mamba_ssm_shim()
     from mamba_ssm.modules.mamba_simple import Mamba as ShimMamba   # the import at DualStreamSEMamba.py:43
     assert ShimMamba is bm.Mamba and pkg.Mamba is bm.Mamba
+
+
+def test_workspace_queries_and_tuning_knobs():
+    """bimamba_*_workspace_bytes reproduce what ops.py allocates (a non-Python host sizes its workspaces from
+    these); the tuning knobs are plain process-wide integers (no getenv on launch paths)."""
+    lib = bm._lib.load()
+    B, ndir, L, D, N = 64, 2, 201, 288, 16
+    nck = -(-L // 8)
+    assert lib.bimamba_scan_fwd_workspace_bytes(B, ndir, L, D, bm._lib.BF16, 1) == B * ndir * nck * D * N * 4 + B * ndir * L * D * 2
+    assert lib.bimamba_scan_fwd_workspace_bytes(B, ndir, L, D, bm._lib.F32, 1) == B * ndir * nck * D * N * 4 + B * ndir * L * D * 4
+    assert lib.bimamba_scan_fwd_workspace_bytes(B, ndir, L, D, bm._lib.BF16, 0) == 0
+    assert lib.bimamba_scan_fwd_workspace_bytes(1, 1, 8, 32, bm._lib.F32, 1) == 8 * 32 * 4       # one chunk: no checkpoints
+    ng = bm._lib.scan_plan(L, D, B * ndir, True)[1]
+    assert lib.bimamba_scan_bwd_workspace_bytes(B, ndir, L, D) == 4 * (B * ng * L * ndir * 2 * N + B * ndir * D * N + 2 * B * ndir * D)
+    assert lib.bimamba_scan_bwd_workspace_bytes(0, 2, 201, 288) == 0
+    assert lib.bimamba_get_tuning(bm._lib.TUNE_SCAN_FWD) == 0
+    with bm._lib.tuning(bm._lib.TUNE_SCAN_FWD, 3):
+        assert lib.bimamba_get_tuning(bm._lib.TUNE_SCAN_FWD) == 3
+    assert lib.bimamba_get_tuning(bm._lib.TUNE_SCAN_FWD) == 0
+    assert lib.bimamba_set_tuning(99, 1) == -1
+    # new round-2 entry points: argument errors are codes
+    assert lib.bimamba_gelu_fwd(None, None, 8, 0, None) == -1
+    assert lib.bimamba_gelu_fwd(None, None, 0, 0, None) == 0
+    assert lib.bimamba_reduce_rows32(None, None, 2, 9, 402, 48, 1, None) == -1
+    assert lib.bimamba_head_pool_bwd(None, None, None, None, None, None, None, None, 2, 5, 144, 1e-5, 0, None) == -1
+    assert lib.bimamba_finalize_param_grads(*([None] * 12), 144, 288, 16, 9, 2, 4, None) == -1

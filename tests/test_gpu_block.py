@@ -82,21 +82,12 @@ def test_bidirectional_block_fp32_vs_oracle(Bsz, L):
         assert rel(prm.grad, pr[name].grad) < 1e-4, name
 
 
-BWD_VARIANTS = {"lane1": {"BIMAMBA_BWD_KERNEL": "lane", "BIMAMBA_BWD_LANES": "1"},
-                "convtile": {"BIMAMBA_CONV_BWD_TILE": "1"},
-                "lane2": {"BIMAMBA_BWD_KERNEL": "lane", "BIMAMBA_BWD_LANES": "2"},
-                "pair": {"BIMAMBA_BWD_KERNEL": "pair"}}
-
-
-@pytest.mark.parametrize("variant", sorted(BWD_VARIANTS))
 @pytest.mark.parametrize("Bsz,L", [(3, 201), (2, 13)])
-def test_bidirectional_block_backward_kernel_variants(variant, Bsz, L, monkeypatch):
-    """The three backward scan kernels (one lane per channel, two lanes per channel, state pairs) and the conv
-    backward's tile fallback forced in turn on the fused block (dt projection inside the kernel, both directions in
-    one launch): fp32, 1e-4 against the oracle."""
-    for k, v in BWD_VARIANTS[variant].items():
-        monkeypatch.setenv(k, v)
-    test_bidirectional_block_fp32_vs_oracle(Bsz, L)
+def test_bidirectional_block_conv_tile_variant(Bsz, L):
+    """The conv backward's shared-memory tile fallback forced (bimamba_set_tuning) on the fused block (dt projection
+    inside the scan kernels, both directions in one launch): fp32, 1e-4 against the oracle."""
+    with bm._lib.tuning(bm._lib.TUNE_CONV_BWD, 1):
+        test_bidirectional_block_fp32_vs_oracle(Bsz, L)
 
 
 def test_block_bf16_autocast_vs_oracle():
@@ -490,3 +481,74 @@ def test_eer_identity_full_scoring_set():
     scale = max(1.0, float(np.abs(s_ref).max()))
     assert out["fp32"][0] < 1e-4 * scale and out["fp32"][1] == eer_ref
     assert out["bf16"][0] < 2e-2 * scale and abs(out["bf16"][1] - eer_ref) < 5e-3
+
+
+def test_fused_adamw_state_dict_round_trip_and_missing_grads():
+    """the optimizer state must survive state_dict() / load_state_dict() (moments AND the step counter), and
+    parameters without a gradient are skipped like torch.optim.AdamW does."""
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 32), (100,), (7, 5)]
+    mk = lambda: [torch.randn(s, generator=torch.Generator().manual_seed(1)).cuda().requires_grad_(True) for s in shapes]
+    a_p, b_p, r_p = mk(), mk(), mk()
+    a = bm.FusedAdamW(a_p, lr=1e-2, weight_decay=0.1)
+    ref = torch.optim.AdamW(r_p, lr=1e-2, weight_decay=0.1)
+    grads = [[torch.randn(s, generator=g).cuda() for s in shapes] for _ in range(6)]
+
+    def feed(params, gs, skip_last=False):
+        for i, (p, gr) in enumerate(zip(params, gs)):
+            p.grad = None if (skip_last and i == len(params) - 1) else gr.clone()
+    for it in range(3):
+        feed(a_p, grads[it]); a.step()
+        feed(r_p, grads[it]); ref.step()
+    sd = a.state_dict()
+    assert float(sd["state"][0]["step"]) == 3.0
+    b = bm.FusedAdamW(b_p, lr=1e-2, weight_decay=0.1)
+    with torch.no_grad():
+        for q, p in zip(b_p, a_p):
+            q.copy_(p)
+    b.load_state_dict(sd)                       # resume into a fresh optimizer BEFORE its first step
+    for it in range(3, 6):
+        feed(b_p, grads[it]); b.step()
+        feed(r_p, grads[it]); ref.step()
+    for q, r in zip(b_p, r_p):
+        assert rel(q, r) < 1e-6
+    # a torch.optim.AdamW state_dict loads too
+    c_p = mk()
+    c = bm.FusedAdamW(c_p, lr=1e-2, weight_decay=0.1)
+    with torch.no_grad():
+        for q, p in zip(c_p, r_p):
+            q.copy_(p)
+    c.load_state_dict(ref.state_dict())
+    feed(c_p, grads[0]); c.step()
+    feed(r_p, grads[0]); ref.step()
+    for q, r in zip(c_p, r_p):
+        assert rel(q, r) < 1e-6
+    # a parameter without a gradient is left untouched
+    before = c_p[-1].detach().clone()
+    feed(c_p, grads[1], skip_last=True); c.step()
+    assert torch.equal(c_p[-1], before)
+
+
+def test_graphed_train_step_construction_does_not_train():
+    """building the runner (3 warm-up steps) must not move the weights, the moments or the step count."""
+    torch.manual_seed(2)
+    net = bm.BiMambaBackend(144, 1, 16).cuda()
+    params = list(net.backbone_layers.parameters())
+    opt = bm.FusedAdamW(params, lr=1e-2)
+    before = [p.detach().clone() for p in params]
+
+    def zero():
+        for p in params:
+            p.grad = None
+
+    def loss_fn(x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return net.forward_features(x).float().square().mean()
+    runner = bm.GraphedTrainStep(loss_fn, torch.randn(2, 40, 144, device="cuda"), zero, opt, warmup=3)
+    for p, q in zip(params, before):
+        assert torch.equal(p, q)
+    assert float(opt.state_dict()["state"][0]["step"]) == 0.0
+    runner.run()
+    torch.cuda.synchronize()
+    assert float(opt.state_dict()["state"][0]["step"]) == 1.0
+    assert any(not torch.equal(p, q) for p, q in zip(params, before))

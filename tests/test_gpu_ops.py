@@ -148,11 +148,14 @@ def test_causal_conv1d(dtype, L, act):
 
 
 @pytest.mark.parametrize("D,force_tile", [(20, True), (18, False), (288, True)])
-def test_causal_conv1d_backward_tile_kernel(D, force_tile, monkeypatch):
+def test_causal_conv1d_backward_tile_kernel(D, force_tile):
     """The shared-memory tile backward (fallback for rows that are not addressable as 4-channel vectors) against the
-    oracle: forced by environment for vector-friendly widths, taken automatically for D = 18."""
-    if force_tile:
-        monkeypatch.setenv("BIMAMBA_CONV_BWD_TILE", "1")
+    oracle: forced through bimamba_set_tuning for vector-friendly widths, taken automatically for D = 18."""
+    with bm._lib.tuning(bm._lib.TUNE_CONV_BWD, 1 if force_tile else 0):
+        _conv_bwd_case(D)
+
+
+def _conv_bwd_case(D):
     g = torch.Generator().manual_seed(D)
     Bsz, K, L = 2, 4, 77
     x = torch.randn(Bsz, D, L, generator=g)
@@ -269,46 +272,42 @@ def test_colsum(rows, cols):
     assert rel(out, x.double().sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("lanes", ["1", "2", "3"])
+@pytest.mark.parametrize("variant", [1, 3])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_scan_forward_variants(lanes, dtype, monkeypatch):
-    """The forward kernels (1: one lane per channel, wide CTAs; 2: two lanes per channel; 3: one lane per channel, one
-    warp per CTA) are forced in turn on the same inputs; the size-based dispatch must not change results beyond
+def test_scan_forward_variants(variant, dtype):
+    """The two forward kernels (1: one lane per channel, wide CTAs; 3: one lane per channel, one warp per CTA) are
+    forced in turn on the same inputs (bimamba_set_tuning); the size-based dispatch must not change results beyond
     rounding."""
-    monkeypatch.setenv("BIMAMBA_FWD_LANES", lanes)
-    for L, D in ((201, 288), (37, 40), (499, 17)):
-        errs = _run_both(2, D, L, dtype, seed=L + D)
-        assert max(errs.values()) < TOL[dtype], (lanes, L, D, errs)
+    with bm._lib.tuning(bm._lib.TUNE_SCAN_FWD, variant):
+        for L, D in ((201, 288), (37, 40), (499, 17)):
+            errs = _run_both(2, D, L, dtype, seed=L + D)
+            assert max(errs.values()) < TOL[dtype], (variant, L, D, errs)
 
 
-@pytest.mark.parametrize("variant", ["lane1", "lane2", "pair"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_scan_backward_variants(variant, dtype, monkeypatch):
-    """The three backward kernels (one lane per channel with the chunk history in registers; two lanes per channel -
-    small problems; the state-pair kernel) are forced in turn on the same inputs."""
-    monkeypatch.setenv("BIMAMBA_BWD_KERNEL", "pair" if variant == "pair" else "lane")
-    if variant != "pair":
-        monkeypatch.setenv("BIMAMBA_BWD_LANES", variant[-1])
+def test_scan_backward_shapes(dtype):
+    """The backward kernel on ragged shapes: channel counts that are not multiples of the 32-channel group or of the
+    vector width, a single 8-step chunk, and every optional operand absent."""
     for L, D in ((201, 288), (37, 40), (499, 17), (8, 33)):
         errs = _run_both(2, D, L, dtype, seed=L + D)
-        assert max(errs.values()) < TOL[dtype], (variant, L, D, errs)
+        assert max(errs.values()) < TOL[dtype], (L, D, errs)
     errs = _run_both(2, 40, 77, dtype, with_z=False, with_D=False, with_bias=False, softplus=False, seed=5)
-    assert max(errs.values()) < TOL[dtype], (variant, errs)
+    assert max(errs.values()) < TOL[dtype], errs
 
 
-@pytest.mark.parametrize("kernel", ["tile", "persist"])
-def test_gemm_nt_kernel_variants(kernel, monkeypatch):
-    """Both tcgen05 kernels (one tile per CTA; persistent warp-specialised with two TMEM accumulators) forced in
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_gemm_nt_kernel_variants(kernel):
+    """Both tcgen05 kernels (1: one tile per CTA; 2: persistent warp-specialised with two TMEM accumulators) forced in
     turn, incl. the 192-column tiles and a tile list several times the SM count."""
-    monkeypatch.setenv("BIMAMBA_GEMM_KERNEL", kernel)
-    for M, N, K in ((12864, 576, 144), (40000, 288, 48), (300, 144, 576), (70000, 48, 288)):
-        g = torch.Generator().manual_seed(M + N)
-        A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
-        B = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
-        bias = torch.randn(N, generator=g).cuda()
-        out = bm.ops.gemm_nt(A, B, bias=bias, out_dtype=torch.float32)
-        ref = A.double() @ B.double().t() + bias.double()
-        assert rel(out, ref) < 1e-5, (kernel, M, N, K)
+    with bm._lib.tuning(bm._lib.TUNE_GEMM_KERNEL, kernel):
+        for M, N, K in ((12864, 576, 144), (40000, 288, 48), (300, 144, 576), (70000, 48, 288)):
+            g = torch.Generator().manual_seed(M + N)
+            A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+            B = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+            bias = torch.randn(N, generator=g).cuda()
+            out = bm.ops.gemm_nt(A, B, bias=bias, out_dtype=torch.float32)
+            ref = A.double() @ B.double().t() + bias.double()
+            assert rel(out, ref) < 1e-5, (kernel, M, N, K)
 
 
 @pytest.mark.parametrize("M,N1,N2", [(12864, 576, 144), (25728, 288, 48), (12864, 576, 144), (130, 128, 16), (1000, 144, 576),
