@@ -9,13 +9,15 @@ from .fusion import DualStreamFusion, SELayer
 from .graph import GraphedForward, GraphedTrainStep
 from .mamba_simple import Mamba
 from .optim import FusedAdamW
+from .training import FGM, LoRALinear, Phase6TrainStep, apply_lora, freeze_batch_norm_stats, mixup_batch, mixup_loss
 from .ops import (BiMambaInnerFn, CausalConv1dFn, SelectiveScanFn, bimamba_inner_fn, causal_conv1d_fn,
                   selective_scan_fn)
 
 __all__ = [
     "Mamba", "PN_BiMambas_Encoder", "BiMambaBackend", "BiMambaInnerFn", "CausalConv1dFn", "SelectiveScanFn",
     "bimamba_inner_fn", "causal_conv1d_fn", "selective_scan_fn", "install_mamba_ssm_shim",
-    "DualStreamFusion", "SELayer", "FlatGradBucket", "shard_batch", "GraphedForward", "GraphedTrainStep", "FusedAdamW",
+    "DualStreamFusion", "SELayer", "FGM", "LoRALinear", "Phase6TrainStep", "apply_lora", "freeze_batch_norm_stats", "mixup_batch", "mixup_loss",
+    "FlatGradBucket", "shard_batch", "GraphedForward", "GraphedTrainStep", "FusedAdamW",
 ]
 
 

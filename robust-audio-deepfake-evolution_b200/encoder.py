@@ -56,21 +56,24 @@ class BiMambaBackend(nn.Module):
         return f_fused
 
     def forward(self, f_fused):
-        f_fused = self.forward_features(f_fused)
-        if not torch.is_grad_enabled() and not self.training and f_fused.shape[-1] <= 256:
-            # scoring (src/main.py:958-995): norm_f, attention pooling and the classifier in one launch
-            feats, logits = head_fwd(f_fused, self.norm_f.weight, self.norm_f.bias, self.attention_pool.weight,
-                                     self.attention_pool.bias, self.classifier.weight, self.classifier.bias,
-                                     self.norm_f.eps)
-            return feats.to(f_fused.dtype), logits.to(f_fused.dtype)
-        if f_fused.shape[-1] <= 256:
-            # training: norm_f + attention pooling as one kernel forward and one backward (:759-763)
-            features = head_pool_fn(f_fused, self.norm_f.weight, self.norm_f.bias, self.attention_pool.weight,
-                                    self.attention_pool.bias, self.norm_f.eps).to(f_fused.dtype)
-        else:
-            f_fused = layer_norm_fn(f_fused, self.norm_f.weight, self.norm_f.bias, self.norm_f.eps,
-                                    out_dtype=f_fused.dtype)                                         # :759
-            attn = F.softmax(self.attention_pool(f_fused), dim=1)                   # :762
-            features = torch.matmul(attn.transpose(1, 2), f_fused).squeeze(1)       # :763
-        features = self.dropout(features)                                           # :764
-        return features, self.classifier(features)                                  # :767
+        return backend_head(self, self.forward_features(f_fused))
+
+
+def backend_head(m, f_fused):
+    """norm_f -> attention pooling -> dropout -> classifier on a module that carries the reference's attribute names
+    (`norm_f`, `attention_pool`, `dropout`, `classifier`; DualStreamSEMamba.py:759-767).  Returns (features, logits)."""
+    if not torch.is_grad_enabled() and not m.training and f_fused.shape[-1] <= 256:
+        # scoring (src/main.py:958-995): norm_f, attention pooling and the classifier in one launch
+        feats, logits = head_fwd(f_fused, m.norm_f.weight, m.norm_f.bias, m.attention_pool.weight,
+                                 m.attention_pool.bias, m.classifier.weight, m.classifier.bias, m.norm_f.eps)
+        return feats.to(f_fused.dtype), logits.to(f_fused.dtype)
+    if f_fused.shape[-1] <= 256:
+        # training: norm_f + attention pooling as one kernel forward and one backward (:759-763)
+        features = head_pool_fn(f_fused, m.norm_f.weight, m.norm_f.bias, m.attention_pool.weight,
+                                m.attention_pool.bias, m.norm_f.eps).to(f_fused.dtype)
+    else:
+        f_fused = layer_norm_fn(f_fused, m.norm_f.weight, m.norm_f.bias, m.norm_f.eps, out_dtype=f_fused.dtype)   # :759
+        attn = F.softmax(m.attention_pool(f_fused), dim=1)                          # :762
+        features = torch.matmul(attn.transpose(1, 2), f_fused).squeeze(1)           # :763
+    features = m.dropout(features)                                                  # :764
+    return features, m.classifier(features)                                         # :767

@@ -119,6 +119,11 @@ def _model_tail_fixtures():
         else:
             for k in ("features", "logits", "cot_logits", "cot_features"):
                 rec.pop(k)
+            # the SincNet stream (DualStreamSEMamba.py:206-273, eval mode, fp32) of this case: waveform and weights, so
+            # the harness's stand-in stream (tools/phase6_model.py) can be checked against f_sinc
+            rec["wav"] = wav.numpy().astype(np.float32)
+            for name, t in model.sinc_stream.state_dict().items():
+                rec["sinc." + name] = t.detach().numpy()
         np.savez_compressed(os.path.join(HERE, f"model_tail_{tag}.npz"), **rec)
         print("model tail", tag, "f_sinc", tuple(f_sinc.shape), "f_fused", tuple(f_fused.shape), "logits", logits.detach().numpy())
 

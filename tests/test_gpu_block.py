@@ -552,3 +552,68 @@ def test_graphed_train_step_construction_does_not_train():
     torch.cuda.synchronize()
     assert float(opt.state_dict()["state"][0]["step"]) == 1.0
     assert any(not torch.equal(p, q) for p, q in zip(params, before))
+
+
+def test_fgm_step_backend_gradients_vs_oracle():
+    """One FGM micro-step of the reference loop (src/main.py:1077-1098) on the CUDA backend: clean backward, attack on the
+    `feature_projection` parameter upstream of the backend, adversarial forward / backward, restore - both passes
+    accumulating into FlatGradBucket(accumulate=True).  The accumulated gradients of every backend parameter equal the
+    fp64 oracle's clean + adversarial gradients (fp32, 1e-4)."""
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(21)
+            self.feature_projection = torch.nn.Linear(24, 144)
+            self.tail = bm.BiMambaBackend(144, 2, 16)
+
+        def forward(self, x):
+            return self.tail(self.feature_projection(x))
+
+    net = Net().cuda().eval()                         # eval: dropout off, the training head is still taken (grad mode on)
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(3, 50, 24, generator=g)
+    y = torch.randint(0, 2, (3,), generator=g)
+    wce = torch.tensor([0.1, 0.9])
+    params = [p for p in net.parameters()]
+    bucket = bm.FlatGradBucket(params, accumulate=True)
+    fgm = bm.FGM(net, "feature_projection", epsilon=0.5)
+    bucket.zero()
+    loss = torch.nn.functional.cross_entropy(net(x.cuda())[1].float(), y.cuda(), weight=wce.cuda())
+    loss.backward()
+    fgm.attack()
+    adv = torch.nn.functional.cross_entropy(net(x.cuda())[1].float(), y.cuda(), weight=wce.cuda())
+    adv.backward()
+    fgm.restore()
+
+    # oracle: same two passes in fp64
+    sd = {k: v.detach().double().cpu() for k, v in net.state_dict().items()}
+    W = sd["feature_projection.weight"].clone().requires_grad_(True)
+    b = sd["feature_projection.bias"].clone().requires_grad_(True)
+    layers = [{k[len(f"tail.backbone_layers.{i}."):]: v.clone().requires_grad_(True) for k, v in sd.items()
+               if k.startswith(f"tail.backbone_layers.{i}.")} for i in range(2)]
+    head = {k[len("tail."):]: v.clone().requires_grad_(True) for k, v in sd.items()
+            if k.startswith(("tail.norm_f", "tail.attention_pool", "tail.classifier"))}
+    leaves = [W, b] + [v for p in layers for v in p.values()] + list(head.values())
+
+    def run(Wv, bv):
+        f = x.double() @ Wv.t() + bv
+        return torch.nn.functional.cross_entropy(orc.backend_ref(layers, head, f)[1], y, weight=wce.double())
+    g1 = torch.autograd.grad(run(W, b), leaves)
+    Wa = (W + 0.5 * g1[0] / g1[0].norm()).detach()
+    ba = (b + 0.5 * g1[1] / g1[1].norm()).detach()
+    W2, b2 = Wa.clone().requires_grad_(True), ba.clone().requires_grad_(True)
+    leaves2 = [W2, b2] + leaves[2:]
+    g2 = torch.autograd.grad(run(W2, b2), leaves2)
+    want = {}
+    names = ["feature_projection.weight", "feature_projection.bias"]
+    names += [f"tail.backbone_layers.{i}.{k}" for i, p in enumerate(layers) for k in p]
+    names += ["tail." + k for k in head]
+    for n, a1, a2 in zip(names, g1, g2):
+        want[n] = a1 + a2
+    assert rel(adv, run(W2, b2)) < 1e-4
+    for n, p in net.named_parameters():
+        if n == "tail.attention_pool.bias":
+            assert float(p.grad.abs().max()) < 1e-5
+        else:
+            assert rel(p.grad, want[n]) < 1e-4, n
+    assert torch.equal(net.feature_projection.weight.detach().cpu().double(), sd["feature_projection.weight"])   # restored
