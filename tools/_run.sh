@@ -1,10 +1,6 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -30
-( time python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err
-tail -4 gpurun_out/bench_full.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_full.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['cpu_baseline'])
-for r in d['roofline_more']: print({k:(round(v,4) if isinstance(v,float) else v) for k,v in r.items() if k not in ('note',)})
-for r in d['scan_sweep']: print(r)
-PY
+set -x
+CMD1="python bench.py --steps 2 --warmup 1 --no-sweep --no-cpu-baseline --no-graph"
+$CMD1 > gpurun_out/plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_launches.csv $CMD1 > gpurun_out/ncu1.log 2>&1
+CMD2="python tools/prof_block.py --iters 2"
+$CMD2 > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"scan_bwd_lane|scan_fwd_warp|gemm_nt_kernel|gemm_tn_kernel|conv_bwd_seg" -s 30 -c 24 -o gpurun_out/r2_kernels $CMD2 > gpurun_out/ncu2.log 2>&1
+ls -la gpurun_out | tail -8
