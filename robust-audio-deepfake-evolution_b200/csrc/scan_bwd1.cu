@@ -56,9 +56,10 @@ struct LaneSmem {
   static constexpr size_t part_f = kNW > 1 ? (size_t)kNW * kLT * 32 : 0;
   static constexpr size_t el_f = (size_t)2 * kLT * NT;              // delta, softplus' (per lane)
   static constexpr size_t xf_f = (size_t)kLT * kXW;
+  static constexpr size_t wdt_f = (size_t)NT * 20;                  // dt_proj.weight rows, stride 12 or 20 floats per lane
   static constexpr size_t xr_e = (size_t)2 * kLT * kXW;             // T
   static constexpr size_t act_buf_e = (size_t)kNAct * kLT * G;      // T, one buffer
-  static constexpr size_t total = ck_f4 * 16 + (red_f + part_f + el_f + xf_f) * 4 + (xr_e + 2 * act_buf_e) * sizeof(T);
+  static constexpr size_t total = ck_f4 * 16 + (red_f + part_f + el_f + xf_f + wdt_f) * 4 + (xr_e + 2 * act_buf_e) * sizeof(T);
 };
 
 template <typename T, int kMode, int kNW, int kSplit>
@@ -105,7 +106,8 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
   float* s_part = s_red + SM::red_f;                                // [kNW][8][32]  (kNW > 1)
   float* s_el = s_part + SM::part_f;                                // [2][8][NT]   delta, softplus'
   float* s_xf = s_el + SM::el_f;                                    // [8][kXW]     rows as fp32
-  T* s_xr = reinterpret_cast<T*>(s_xf + SM::xf_f);                  // [2][8][kXW]  rows as staged
+  float* s_wdt = s_xf + SM::xf_f;                                   // [NT][kWS]    this lane's dt_proj.weight row
+  T* s_xr = reinterpret_cast<T*>(s_wdt + SM::wdt_f);                // [2][8][kXW]  rows as staged
   T* s_act = s_xr + SM::xr_e;                                       // [2][5][8][G]
 
   const bool dim_vec = (p.dim % kV) == 0;
@@ -203,7 +205,8 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
 
   // ---- per-channel constants and accumulators (this lane's NS states)
   float2 A2[NP], m[NP], dAa[NP];
-  float2 wdt[2 * R4];
+  constexpr int kWS = kMode == 1 ? 12 : 20;      // floats per lane row of s_wdt: 16-byte reads without bank conflicts
+  float* const my_w = s_wdt + tid * kWS;
   float bias = 0.f, Dd = 0.f, dDacc = 0.f, dbacc = 0.f;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -211,8 +214,10 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
     m[j] = make_float2(0.f, 0.f);
     dAa[j] = make_float2(0.f, 0.f);
   }
+  if (!expl) {
 #pragma unroll
-  for (int q = 0; q < 2 * R4; ++q) wdt[q] = make_float2(0.f, 0.f);
+    for (int r = 0; r < 4 * R4; ++r) my_w[r] = 0.f;
+  }
   if (ok) {
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
@@ -222,10 +227,9 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
     if (p.delta_bias) bias = __ldg(p.delta_bias + d);
     if (p.D) Dd = __ldg(p.D + d);
     if (!expl) {
-      float* w = reinterpret_cast<float*>(wdt);
 #pragma unroll
       for (int r = 0; r < 4 * R4; ++r)
-        if (r < R) w[r] = __ldg(p.Wdt + (int64_t)d * R + r);
+        if (r < R) my_w[r] = __ldg(p.Wdt + (int64_t)d * R + r);   // written and read by this lane only
     }
   }
   // dB|dC exchange: row = channel, 8 pieces of 4 floats; with two lanes per channel the halves' pieces interleave
@@ -274,16 +278,20 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
     const int64_t off0 = trow0 * p.out_ts;
     float* const pB0 = partB + trow0 * pb_ts + mycol;
 
-    // ---- re-run the chunk forward from its checkpoint, keeping h[0..6] in registers
-    float2 h[NP], hh[kLT - 1][NP];
+    // ---- re-run the chunk forward from its checkpoint keeping h[0..6] in registers (7 x 16), then walk it backwards.
+    // (Keeping only h[3] + three states at a time and recomputing steps 0..2 - 48 registers fewer, capped at 168 so
+    // that 12 warps fit per SM - spilled 416 bytes and ran 1.4x slower: profiles/r2_history.md.)
+    float2 h[NP];
+    auto load_ck = [&](float2 (&dst)[NP]) {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float4 v = ckp[q * NT];
-      h[2 * q] = make_float2(v.x, v.y);
-      h[2 * q + 1] = make_float2(v.z, v.w);
-    }
+      for (int q = 0; q < NQ; ++q) {
+        const float4 v = ckp[q * NT];
+        dst[2 * q] = make_float2(v.x, v.y);
+        dst[2 * q + 1] = make_float2(v.z, v.w);
+      }
+    };
+    load_ck(h);
     // delta and softplus' of the chunk's 8 steps first: eight independent chains, no branches (the flags select)
-    float dl[kLT];
 #pragma unroll
     for (int i = 0; i < kLT; ++i) {
       const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW);
@@ -295,8 +303,9 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
 #pragma unroll
         for (int q = 0; q < R4; ++q) {
           const float4 x = xr[8 + q];
-          acc0 = __ffma2_rn(wdt[2 * q], make_float2(x.x, x.y), acc0);
-          acc1 = __ffma2_rn(wdt[2 * q + 1], make_float2(x.z, x.w), acc1);
+          const float4 w = reinterpret_cast<const float4*>(my_w)[q];
+          acc0 = __ffma2_rn(make_float2(w.x, w.y), make_float2(x.x, x.y), acc0);
+          acc1 = __ffma2_rn(make_float2(w.z, w.w), make_float2(x.z, x.w), acc1);
         }
         const float2 acc = __fadd2_rn(acc0, acc1);
         draw = acc.x + acc.y;
@@ -305,15 +314,13 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
       const float sgd = draw > 20.f ? 1.f : sigmoid_f(draw);
       float delta = softplus ? spl : draw;
       delta = i < nvalid ? delta : 0.f;   // steps past the end of the sequence are the identity
-      dl[i] = delta;
       myel[i * NT] = delta;
       myel[(kLT + i) * NT] = softplus ? sgd : 1.f;
     }
-#pragma unroll
-    for (int i = 0; i < kLT; ++i) {
+    auto fwd_step = [&](const int i) {
       const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW);
       const float u = to_f(sa[i * G]);
-      const float delta = dl[i];
+      const float delta = myel[i * NT];   // written by this thread above
       const float du = delta * u;
       const float2 dd = make_float2(delta, delta), duu = make_float2(du, du);
 #pragma unroll
@@ -330,15 +337,9 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
           h[2 * q + 1] = __ffma2_rn(a, h[2 * q + 1], __fmul2_rn(duu, make_float2(Bq.z, Bq.w)));
         }
       }
-      if (i < kLT - 1) {
-#pragma unroll
-        for (int j = 0; j < NP; ++j) hh[i][j] = h[j];
-      }
-    }
-
+    };
     // ---- reverse recurrence over the chunk:  dh_i = g_i C_i + m_{i+1},  m_i = a_i dh_i
-#pragma unroll
-    for (int i = kLT - 1; i >= 0; --i) {
+    auto rev_step = [&](const int i, const float2 (&hc_)[NP], const float2 (&hp_)[NP]) {
       const float4* xr = reinterpret_cast<const float4*>(s_xf + i * kXW);
       const float delta = myel[i * NT], sp = myel[(kLT + i) * NT];   // written by this thread
       const float u = to_f(sa[i * G]);
@@ -360,8 +361,6 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const float4 Bq = xr[half * NQ + q], Cq = xr[4 + half * NQ + q];
-        float4 hpq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i == 0) hpq = ckp[q * NT];
         float2 dBv[2], dCv[2];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -372,8 +371,8 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
           const float2 a = make_float2(ex2_approx(x.x), ex2_approx(x.y));
           const float2 dh = __ffma2_rn(gg, C2, m[j]);
           m[j] = __fmul2_rn(a, dh);
-          const float2 hp = i == 0 ? (s ? make_float2(hpq.z, hpq.w) : make_float2(hpq.x, hpq.y)) : hh[i == 0 ? 0 : i - 1][j];
-          const float2 hc = i == kLT - 1 ? h[j] : hh[i == kLT - 1 ? 0 : i][j];
+          const float2 hp = hp_[j];
+          const float2 hc = hc_[j];
           const float2 da = __fmul2_rn(m[j], hp);
           dAa[j] = __ffma2_rn(da, dd, dAa[j]);
           sAv[s] = __ffma2_rn(da, A2[j], sAv[s]);   // sum_n dh a h[t-1] A (x log2e; scaled back below)
@@ -424,6 +423,23 @@ __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd
         }
       }
       __syncwarp();   // the rows are rewritten by the next step
+    };
+    {
+      float2 hh[kLT - 1][NP];
+#pragma unroll
+      for (int i = 0; i < kLT; ++i) {
+        fwd_step(i);
+        if (i < kLT - 1) {
+#pragma unroll
+          for (int j = 0; j < NP; ++j) hh[i][j] = h[j];
+        }
+      }
+      rev_step(7, h, hh[6]);
+#pragma unroll
+      for (int i = kLT - 2; i >= 1; --i) rev_step(i, hh[i], hh[i - 1]);
+      float2 hck[NP];
+      load_ck(hck);
+      rev_step(0, hh[0], hck);
     }
     if constexpr (kNW > 1) {      // add the warps in fixed order
       __syncthreads();

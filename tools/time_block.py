@@ -17,7 +17,11 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--frames", type=int, default=201)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--iters", type=int, default=12)
+ap.add_argument("--tune", default="", help="knob=value,... (bimamba_set_tuning)")
 a = ap.parse_args()
+for kv in filter(None, a.tune.split(",")):
+    k, v = kv.split("=")
+    bm._lib.load().bimamba_set_tuning(int(k), int(v))
 dt = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}[a.dtype]
 torch.manual_seed(1234)
 m = bm.Mamba(144, 16).cuda()

@@ -11,7 +11,11 @@ ap.add_argument("--batch", type=int, default=2048)
 ap.add_argument("--L", type=int, default=256)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--fwd-only", action="store_true")
+ap.add_argument("--tune", default="")
 a = ap.parse_args()
+for kv in filter(None, a.tune.split(",")):
+    k, v = kv.split("=")
+    bm._lib.load().bimamba_set_tuning(int(k), int(v))
 dt = {"bf16": torch.bfloat16, "f32": torch.float32}[a.dtype]
 g = torch.Generator(device="cuda").manual_seed(0)
 B, D, L, N = a.batch, 288, a.L, 16
