@@ -4,7 +4,7 @@ the hyphens import it with `importlib.import_module("robust-audio-deepfake-evolu
 through the top-level alias module `bimamba_b200`."""
 from . import _lib
 from .dist import FlatGradBucket, shard_batch
-from .encoder import BiMambaBackend, PN_BiMambas_Encoder
+from .encoder import BiMambaBackend, PN_BiMambas_Encoder, backend_head
 from .fusion import DualStreamFusion, SELayer
 from .graph import GraphedForward, GraphedTrainStep
 from .mamba_simple import Mamba
@@ -14,7 +14,7 @@ from .ops import (BiMambaInnerFn, CausalConv1dFn, SelectiveScanFn, bimamba_inner
                   selective_scan_fn)
 
 __all__ = [
-    "Mamba", "PN_BiMambas_Encoder", "BiMambaBackend", "BiMambaInnerFn", "CausalConv1dFn", "SelectiveScanFn",
+    "Mamba", "PN_BiMambas_Encoder", "BiMambaBackend", "backend_head", "BiMambaInnerFn", "CausalConv1dFn", "SelectiveScanFn",
     "bimamba_inner_fn", "causal_conv1d_fn", "selective_scan_fn", "install_mamba_ssm_shim",
     "DualStreamFusion", "SELayer", "FGM", "LoRALinear", "Phase6TrainStep", "apply_lora", "freeze_batch_norm_stats", "mixup_batch", "mixup_loss",
     "FlatGradBucket", "shard_batch", "GraphedForward", "GraphedTrainStep", "FusedAdamW",

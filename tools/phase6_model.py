@@ -131,4 +131,4 @@ class Phase6Model(nn.Module):
         for layer in self.backbone_layers:
             f_fused = layer(f_fused)
         import bimamba_b200 as bm
-        return bm.encoder.backend_head(self, f_fused)
+        return bm.backend_head(self, f_fused)
