@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 5
+#define BIMAMBA_ABI_VERSION 6
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -267,6 +267,15 @@ int bimamba_cast_transpose(const float* src, void* dst, void* dstT, int rows, in
  * contiguous elements of `dtype` (16-byte aligned bases). */
 int bimamba_gelu_fwd(const void* x, void* y, int64_t n, int dtype, bimamba_stream_t stream);
 int bimamba_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, bimamba_stream_t stream);
+
+/* fp32-accurate products on the bf16 tensor cores (the 1e-4 parity mode and fp32 scoring, src/main.py:973-976): splits
+ * an fp32 (rows, cols) matrix into three bf16 terms x = hi + mid + lo (24 bits) written as six blocks,
+ *   side 0: [hi | mid | lo | hi | hi | mid]     side 1: [hi | hi | hi | mid | lo | mid]
+ * block b of element (r, c) at dst[b * block_stride + r * ld_dst + c].  With block_stride = cols (ld_dst = 6 * cols) the
+ * blocks extend the contraction axis of bimamba_gemm_nt: gemm_nt(split(A, 0), split(B, 1)) = A . B^T to ~2^-24; with
+ * block_stride = rows * ld_dst they extend the row axis bimamba_gemm_tn contracts over. */
+int bimamba_split3_bf16(const float* src, void* dst, int64_t rows, int cols, int64_t ld_src, int64_t ld_dst,
+                        int64_t block_stride, int side, bimamba_stream_t stream);
 
 /* Channel-group sum of the backward scan's [dB | dC] partial rows, written into the first 32 columns of a row matrix:
  *   out[(g * nrows + r) * out_ld + c] = sum_{i < nparts} part[((g * nparts + i) * nrows + r) * 32 + c],  c < 32

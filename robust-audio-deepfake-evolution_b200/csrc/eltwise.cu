@@ -63,6 +63,32 @@ __global__ void __launch_bounds__(256) reduce_rows32_kernel(const float* __restr
   }
 }
 
+// fp32 -> three bf16 terms, x = hi + mid + lo to 24 bits (each residual is exact in fp32), laid out as SIX blocks so
+// that ONE bf16 tensor-core GEMM with fp32 accumulation over the stacked contraction axis gives an fp32-accurate
+// product:   side 0: [hi | mid | lo | hi | hi | mid],  side 1: [hi | hi | hi | mid | lo | mid]
+//   sum_blocks a_blk . b_blk = hi.hi + mid.hi + lo.hi + hi.mid + hi.lo + mid.mid     (dropped terms <= 2^-24 relative)
+// Block b of element (r, c) goes to dst[b * block_stride + r * ld_dst + c]: block_stride = cols stacks the blocks along
+// the columns (K-major operands of gemm_nt), block_stride = rows * ld_dst along the rows (gemm_tn contracts over rows).
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
+                                                     int cols, int64_t ld_src, int64_t ld_dst, int64_t block_stride, int side) {
+  const int64_t total = rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols;
+    const int c = (int)(e - r * cols);
+    const float x = __ldg(src + r * ld_src + c);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    __nv_bfloat16* d = dst + r * ld_dst + c;
+    if (side == 0) {
+      d[0] = hi; d[block_stride] = mid; d[2 * block_stride] = lo; d[3 * block_stride] = hi; d[4 * block_stride] = hi; d[5 * block_stride] = mid;
+    } else {
+      d[0] = hi; d[block_stride] = hi; d[2 * block_stride] = hi; d[3 * block_stride] = mid; d[4 * block_stride] = lo; d[5 * block_stride] = mid;
+    }
+  }
+}
+
 struct FinalizeArgs {
   const float* dA;       // (D, N)       sum_t dh a h delta
   const float* A;        // (D, N)       -exp(A_log)
@@ -189,6 +215,20 @@ extern "C" int bimamba_finalize_param_grads(const float* dA, const float* A, con
   FinalizeArgs a{dA, A, dWxp, dWdt_full, dWo2, dwb, dA_log, dWx, dWdt, dWo, dconv_w, dconv_b, d_inner, d_state, dt_rank, d_model, ndir, d_conv};
   const int total = d_inner * d_state + (dt_rank + 2 * d_state) * d_inner + d_inner * dt_rank + d_model * d_inner + d_inner * (d_conv + 1);
   finalize_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+extern "C" int bimamba_split3_bf16(const float* src, void* dst, int64_t rows, int cols, int64_t ld_src, int64_t ld_dst,
+                                   int64_t block_stride, int side, bimamba_stream_t stream) {
+  if (rows == 0 || cols == 0) return 0;
+  if (!src || !dst || rows < 0 || cols < 0 || side < 0 || side > 1 || ld_src < cols || ld_dst < cols || block_stride < 1) {
+    set_err("split3_bf16: bad arguments");
+    return -1;
+  }
+  split3_kernel<<<ew_blocks(rows * cols, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), rows, cols, ld_src, ld_dst, block_stride, side);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

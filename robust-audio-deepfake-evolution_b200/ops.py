@@ -433,10 +433,41 @@ def _tc_ok(A: torch.Tensor, B: torch.Tensor) -> bool:
             and B.stride(0) % 8 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0 and A.shape[0] > 0)
 
 
+def _split3(t: torch.Tensor, side: int, stack_rows: bool) -> torch.Tensor:
+    """fp32 (rows, cols) -> bf16 six-block split (bimamba_split3_bf16): (rows, 6*cols) for the K-major operands of
+    gemm_nt, (6*rows, cols) for the row-contracted operands of gemm_tn."""
+    lib = _lib.load()
+    rows, cols = t.shape
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    if stack_rows:
+        dst = torch.empty((6 * rows, cols), device=t.device, dtype=torch.bfloat16)
+        ld_dst, block = cols, rows * cols
+    else:
+        dst = torch.empty((rows, 6 * cols), device=t.device, dtype=torch.bfloat16)
+        ld_dst, block = 6 * cols, cols
+    with _timed("split3"):
+        _lib.check(lib.bimamba_split3_bf16(_ptr(t), _ptr(dst), rows, cols, t.stride(0), ld_dst, block, side, _stream()),
+                   "bimamba_split3_bf16")
+    return dst
+
+
+def _f32_tc_ok(A: torch.Tensor, B: torch.Tensor, k_mult: int) -> bool:
+    """fp32 operands that the split path can take: contiguous rows, contraction / row widths that keep the bf16
+    blocks 16-byte aligned."""
+    return (A.dtype == torch.float32 and B.dtype == torch.float32 and A.dim() == 2 and B.dim() == 2 and A.is_cuda
+            and A.shape[0] > 0 and A.shape[1] % k_mult == 0 and B.shape[1] % k_mult == 0 and A.shape[1] > 0)
+
+
 def gemm_nt(A, B, bias=None, addend=None, out_dtype=None, out=None):
     """A (M, K) . B (N, K)^T (+ bias (N) fp32) (+ addend (M, N)) -> (M, N).  bf16 / fp16 operands run on this
-    repository's tcgen05 kernel; fp32 operands (the 1e-4 parity mode) stay on the fp32 library GEMM."""
+    repository's tcgen05 kernel; fp32 operands (the 1e-4 parity mode, fp32 scoring) are split into three bf16 terms each and
+    run on the same kernel with six K blocks (fp32-accurate, bimamba_split3_bf16).  Only shapes whose contraction width is
+    not a multiple of 4 fall back to the framework product."""
     out_dtype = out_dtype or (out.dtype if out is not None else A.dtype)
+    if _f32_tc_ok(A, B, 4) and A.shape[1] == B.shape[1] and out_dtype == torch.float32:
+        # fp32 operands: three-term bf16 split of both, six K blocks, one tcgen05 GEMM with fp32 accumulation
+        return gemm_nt(_split3(A, 0, False), _split3(B, 1, False), bias, addend, torch.float32, out)
     if not _tc_ok(A, B):
         C_ = torch.mm(A, B.t()).to(out_dtype)
         if bias is not None:
@@ -467,7 +498,11 @@ def gemm_nt(A, B, bias=None, addend=None, out_dtype=None, out=None):
 
 def gemm_tn(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     """A (M, N1)^T . B (M, N2) -> (N1, N2) fp32: the weight gradient dY^T X on the tcgen05 kernel (MN-major operands,
-    deterministic split over the M rows).  fp32 / misaligned operands use the library product."""
+    deterministic split over the M rows).  fp32 operands are split into three bf16 terms stacked along the contracted rows;
+    only misaligned operands use the framework product."""
+    if _f32_tc_ok(A, B, 8) and A.shape[0] == B.shape[0]:
+        # fp32 operands: the six split blocks are stacked along the contracted rows
+        return gemm_tn(_split3(A, 0, True), _split3(B, 1, True))
     if not _tc_ok(A, B):
         return mm_f32(A.t(), B)
     lib = _lib.load()
