@@ -395,3 +395,27 @@ def test_layernorm_wide_rows(C_):
     assert rel(out, ref) < 1e-5
     for a, r in zip(dev_in, ref_in):
         assert rel(a.grad, r.grad) < 1e-5
+
+
+def test_fp32_products_on_the_tensor_cores():
+    """fp32 operands take the three-term bf16 split (bimamba_split3_bf16) and the same tcgen05 kernels: fp32-level accuracy
+    against fp64 for the forward / data-gradient product (blocks along K) and the weight-gradient product (blocks along
+    the contracted rows), with bias, an addend and a strided output."""
+    g = torch.Generator().manual_seed(11)
+    for M, N, K in ((12864, 576, 144), (515, 48, 288), (300, 144, 1024), (58, 144, 64)):
+        A = torch.randn(M, K, generator=g).cuda()
+        B = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        bias = torch.randn(N, generator=g).cuda()
+        add = torch.randn(M, N, generator=g).cuda()
+        out = bm.ops.gemm_nt(A, B, bias=bias, addend=add)
+        assert out.dtype == torch.float32
+        assert rel(out, A.double() @ B.double().t() + bias.double() + add.double()) < 2e-6, (M, N, K)
+    buf = torch.zeros(515, 48, device="cuda")
+    A = torch.randn(515, 288, generator=g).cuda()
+    W = (torch.randn(16, 288, generator=g) / 17).cuda()
+    bm.ops.gemm_nt(A, W, out=buf[:, 32:])
+    assert rel(buf[:, 32:], A.double() @ W.double().t()) < 2e-6 and float(buf[:, :32].abs().max()) == 0.0
+    for M, N1, N2 in ((12864, 576, 144), (25728, 288, 48), (130, 128, 16)):
+        A = torch.randn(M, N1, generator=g).cuda()
+        B = torch.randn(M, N2, generator=g).cuda()
+        assert rel(bm.ops.gemm_tn(A, B), A.double().t() @ B.double()) < 2e-6, (M, N1, N2)
