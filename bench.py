@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scan sweep points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tune", default="", help="knob=value,... forwarded to bimamba_set_tuning (A/B measurements)")
     ap.add_argument("--comm", default="overlap", choices=["overlap", "graph", "eager"],
                     help="N > 1: gradient all-reduce per encoder layer inside the step graph, overlapping the remaining "
                          "backward (default); one all-reduce inside the graph; or launched after the graph (round 1)")
@@ -330,6 +331,9 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import bimamba_b200 as bm
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        bm._lib.load().bimamba_set_tuning(int(k), int(v))
 
     torch.manual_seed(1234)
     model = bm.BiMambaBackend(D_MODEL, N_LAYERS, D_STATE).cuda()

@@ -124,7 +124,8 @@ const char* bimamba_last_error(void);
 #define BIMAMBA_TUNE_GEMM_KERNEL 2  /* 1 = one tile per CTA, 2 = persistent warp-specialised                       */
 #define BIMAMBA_TUNE_GEMM_BN 3      /* tile width override                                                         */
 #define BIMAMBA_TUNE_GEMM_STAGES 4  /* TMA ring depth override                                                     */
-#define BIMAMBA_TUNE_COUNT 5
+#define BIMAMBA_TUNE_PDL 5          /* 1 = launch without programmatic dependent launch (A/B measurements)         */
+#define BIMAMBA_TUNE_COUNT 6
 int bimamba_set_tuning(int knob, int value);
 int bimamba_get_tuning(int knob);
 

@@ -165,7 +165,7 @@ def scan_plan(seqlen: int, dim: int, rows: int, backward: bool = False):
     return g, (dim + g - 1) // g, n
 
 
-TUNE_SCAN_FWD, TUNE_CONV_BWD, TUNE_GEMM_KERNEL, TUNE_GEMM_BN, TUNE_GEMM_STAGES = range(5)
+TUNE_SCAN_FWD, TUNE_CONV_BWD, TUNE_GEMM_KERNEL, TUNE_GEMM_BN, TUNE_GEMM_STAGES, TUNE_PDL = range(6)
 
 
 class tuning:

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kConvThreads)
 conv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
                 int batch, int ndir, int dim, int L, int64_t x_bs, int64_t x_ts, int64_t o_bs, int64_t o_ds,
                 int64_t o_ts, int silu) {
+  pdl_prologue();
   const int nvec = (dim + V - 1) / V;
   const int nseg = (L + kSeg - 1) / kSeg;
   const int64_t total = (int64_t)batch * nseg * nvec;
@@ -142,6 +143,7 @@ conv_bwd_tile_kernel(const T* __restrict__ x, const float* __restrict__ w, const
                      const T* __restrict__ dout, T* __restrict__ dx, const T* __restrict__ dz_in, T* __restrict__ dz_out,
                      float* __restrict__ part, int batch, int ndir, int dim, int L, int64_t x_bs, int64_t x_ts,
                      int64_t g_bs, int64_t g_ds, int64_t g_ts, int64_t dx_bs, int64_t dx_ts, int silu, int vec) {
+  pdl_prologue();
   constexpr int H = K - 1;
   constexpr int XR = kBwdT + 4 * H, GR = kBwdT + 2 * H;   // rows of the x and g tiles
   constexpr int kV = 16 / sizeof(T);
@@ -269,6 +271,7 @@ template <int RL>
 __global__ void __launch_bounds__(256)
 reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int64_t groups, int64_t rows, int64_t cols,
               int64_t part_gs, int64_t row_stride, int64_t out_gs, int dt, int accumulate) {
+  pdl_prologue();
   constexpr int CPB = 256 / RL;
   __shared__ float sm[RL][CPB + 1];
   const int cx = threadIdx.x % CPB, ry = threadIdx.x / CPB;
@@ -302,6 +305,7 @@ constexpr int kColRows = 256;
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, float* __restrict__ part, int64_t rows, int cols, int64_t ld) {
+  pdl_prologue();
   __shared__ float sm[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -335,6 +339,7 @@ conv_bwd_seg_kernel(const T* __restrict__ x, const float* __restrict__ w, const 
                     const T* __restrict__ dout, T* __restrict__ dx, const T* __restrict__ dz_in, T* __restrict__ dz_out,
                     float* __restrict__ part, int batch, int ndir, int dim, int L, int64_t x_bs, int64_t x_ts,
                     int64_t g_bs, int64_t g_ds, int64_t g_ts, int64_t dx_bs, int64_t dx_ts, int silu) {
+  pdl_prologue();
   constexpr int K = 4, H = 3, V = 4;
   const int nvec = dim / V;
   const int nseg = (L + kBwdT - 1) / kBwdT;
@@ -471,9 +476,9 @@ static void launch_conv_fwd(const void* x, const float* w, const float* bias, vo
   const T* xp = reinterpret_cast<const T*>(x);
   T* op = reinterpret_cast<T*>(out);
   switch (width) {
-    case 2: conv_fwd_kernel<T, V, 2><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, op, batch, ndir, dim, L, x_bs, x_ts, o_bs, o_ds, o_ts, silu); break;
-    case 3: conv_fwd_kernel<T, V, 3><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, op, batch, ndir, dim, L, x_bs, x_ts, o_bs, o_ds, o_ts, silu); break;
-    default: conv_fwd_kernel<T, V, 4><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, op, batch, ndir, dim, L, x_bs, x_ts, o_bs, o_ds, o_ts, silu); break;
+    case 2: launch_k(conv_fwd_kernel<T, V, 2>, blocks, kConvThreads, 0, st, xp, w, bias, op, batch, ndir, dim, L, x_bs, x_ts, o_bs, o_ds, o_ts, silu); break;
+    case 3: launch_k(conv_fwd_kernel<T, V, 3>, blocks, kConvThreads, 0, st, xp, w, bias, op, batch, ndir, dim, L, x_bs, x_ts, o_bs, o_ds, o_ts, silu); break;
+    default: launch_k(conv_fwd_kernel<T, V, 4>, blocks, kConvThreads, 0, st, xp, w, bias, op, batch, ndir, dim, L, x_bs, x_ts, o_bs, o_ds, o_ts, silu); break;
   }
 }
 
@@ -490,9 +495,9 @@ static void launch_conv_bwd(const void* x, const float* w, const float* bias, co
   T* dxp = reinterpret_cast<T*>(dx);
   T* zo = reinterpret_cast<T*>(dz_out);
   switch (width) {
-    case 2: conv_bwd_tile_kernel<T, 2><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
-    case 3: conv_bwd_tile_kernel<T, 3><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
-    default: conv_bwd_tile_kernel<T, 4><<<blocks, kConvThreads, 0, st>>>(xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
+    case 2: launch_k(conv_bwd_tile_kernel<T, 2>, blocks, kConvThreads, 0, st, xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
+    case 3: launch_k(conv_bwd_tile_kernel<T, 3>, blocks, kConvThreads, 0, st, xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
+    default: launch_k(conv_bwd_tile_kernel<T, 4>, blocks, kConvThreads, 0, st, xp, w, bias, gp, dxp, zi, zo, part, batch, ndir, dim, L, x_bs, x_ts, g_bs, g_ds, g_ts, dx_bs, dx_ts, silu, vec); break;
   }
 }
 
@@ -558,7 +563,7 @@ extern "C" int bimamba_causal_conv1d_bwd(const void* x, const float* weight, con
   if (seg4) {
     const int64_t total = (int64_t)batch * conv_bwd_time_tiles(seqlen) * (dim / 4);
     const unsigned blocks = (unsigned)((total + kConvThreads - 1) / kConvThreads);
-#define CONV_SEG(T) conv_bwd_seg_kernel<T><<<blocks, kConvThreads, 0, st>>>(reinterpret_cast<const T*>(x), weight, bias, reinterpret_cast<const T*>(dout), reinterpret_cast<T*>(dx), reinterpret_cast<const T*>(dz_in), reinterpret_cast<T*>(dz_out), dwb_part, batch, ndir, dim, seqlen, x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts, silu)
+#define CONV_SEG(T) launch_k(conv_bwd_seg_kernel<T>, blocks, kConvThreads, 0, st, reinterpret_cast<const T*>(x), weight, bias, reinterpret_cast<const T*>(dout), reinterpret_cast<T*>(dx), reinterpret_cast<const T*>(dz_in), reinterpret_cast<T*>(dz_out), dwb_part, batch, ndir, dim, seqlen, x_bs, x_ts, dout_bs, dout_ds, dout_ts, dx_bs, dx_ts, silu)
     if (dtype == BIMAMBA_F32) CONV_SEG(float);
     else if (dtype == BIMAMBA_BF16) CONV_SEG(__nv_bfloat16);
     else CONV_SEG(__half);
@@ -589,11 +594,11 @@ extern "C" int bimamba_reduce_partials(const float* part, void* out, int64_t gro
     return (unsigned)(n > 148 * 64 ? 148 * 64 : n);
   };
   if (rows <= 16)
-    reduce_kernel<1><<<nblocks(256), 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
+    launch_k(reduce_kernel<1>, nblocks(256), 256, 0, st, part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
   else if (rows <= 96)
-    reduce_kernel<8><<<nblocks(32), 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
+    launch_k(reduce_kernel<8>, nblocks(32), 256, 0, st, part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
   else
-    reduce_kernel<32><<<nblocks(8), 256, 0, st>>>(part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
+    launch_k(reduce_kernel<32>, nblocks(8), 256, 0, st, part, out, groups, rows, cols, part_gs, row_stride, out_gs, out_dtype, accumulate);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;
@@ -608,9 +613,9 @@ extern "C" int bimamba_colsum(const void* x, float* part, int64_t rows, int cols
   if (rows < 0 || cols < 0 || dtype < 0 || dtype > 2) { set_err("colsum: bad sizes"); return -3; }
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)bimamba_colsum_slices(rows));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == BIMAMBA_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), part, rows, cols, ld);
-  else if (dtype == BIMAMBA_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), part, rows, cols, ld);
-  else colsum_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), part, rows, cols, ld);
+  if (dtype == BIMAMBA_F32) launch_k(colsum_kernel<float>, grid, 256, 0, st, reinterpret_cast<const float*>(x), part, rows, cols, ld);
+  else if (dtype == BIMAMBA_BF16) launch_k(colsum_kernel<__nv_bfloat16>, grid, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x), part, rows, cols, ld);
+  else launch_k(colsum_kernel<__half>, grid, 256, 0, st, reinterpret_cast<const __half*>(x), part, rows, cols, ld);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

@@ -16,6 +16,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // y = gelu(x) (kBwd = false) or y = g * gelu'(x) (kBwd = true); 16-byte vectors, grid-stride.
 template <typename T, bool kBwd>
 __global__ void __launch_bounds__(256) gelu_kernel(const T* __restrict__ x, const T* __restrict__ g, T* __restrict__ y, int64_t n) {
+  pdl_prologue();
   constexpr int kV = 16 / sizeof(T);
   const int64_t nv = n / kV;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) gelu_kernel(const T* __restrict__ x, cons
 template <typename T>
 __global__ void __launch_bounds__(256) reduce_rows32_kernel(const float* __restrict__ part, T* __restrict__ out, int64_t groups,
                                                             int nparts, int64_t nrows, int64_t out_ld) {
+  pdl_prologue();
   const int64_t total = groups * nrows * 8;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(e & 7);
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256) reduce_rows32_kernel(const float* __restr
 // the columns (K-major operands of gemm_nt), block_stride = rows * ld_dst along the rows (gemm_tn contracts over rows).
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
                                                      int cols, int64_t ld_src, int64_t ld_dst, int64_t block_stride, int side) {
+  pdl_prologue();
   const int64_t total = rows * cols;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / cols;
@@ -106,6 +109,7 @@ struct FinalizeArgs {
 };
 
 __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
+  pdl_prologue();
   const int D = a.D, N = a.N, R = a.R, dm = a.dm, K = a.K;
   const int n0 = D * N, n1 = (R + 2 * N) * D, n2 = D * R, n3 = dm * D, n4 = D * K, n5 = D;
   const int total = n0 + n1 + n2 + n3 + n4 + n5;
@@ -152,11 +156,11 @@ extern "C" int bimamba_gelu_fwd(const void* x, void* y, int64_t n, int dtype, bi
   if (!aligned16(x) || !aligned16(y)) { set_err("gelu_fwd: operands must be 16-byte aligned"); return -10; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == BIMAMBA_F32)
-    gelu_kernel<float, false><<<ew_blocks(n / 4, 256), 256, 0, st>>>((const float*)x, nullptr, (float*)y, n);
+    launch_k(gelu_kernel<float, false>, ew_blocks(n / 4, 256), 256, 0, st, (const float*)x, nullptr, (float*)y, n);
   else if (dtype == BIMAMBA_BF16)
-    gelu_kernel<__nv_bfloat16, false><<<ew_blocks(n / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, n);
+    launch_k(gelu_kernel<__nv_bfloat16, false>, ew_blocks(n / 8, 256), 256, 0, st, (const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, n);
   else
-    gelu_kernel<__half, false><<<ew_blocks(n / 8, 256), 256, 0, st>>>((const __half*)x, nullptr, (__half*)y, n);
+    launch_k(gelu_kernel<__half, false>, ew_blocks(n / 8, 256), 256, 0, st, (const __half*)x, nullptr, (__half*)y, n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;
@@ -168,11 +172,11 @@ extern "C" int bimamba_gelu_bwd(const void* x, const void* dy, void* dx, int64_t
   if (!aligned16(x) || !aligned16(dy) || !aligned16(dx)) { set_err("gelu_bwd: operands must be 16-byte aligned"); return -10; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == BIMAMBA_F32)
-    gelu_kernel<float, true><<<ew_blocks(n / 4, 256), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, n);
+    launch_k(gelu_kernel<float, true>, ew_blocks(n / 4, 256), 256, 0, st, (const float*)x, (const float*)dy, (float*)dx, n);
   else if (dtype == BIMAMBA_BF16)
-    gelu_kernel<__nv_bfloat16, true><<<ew_blocks(n / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, n);
+    launch_k(gelu_kernel<__nv_bfloat16, true>, ew_blocks(n / 8, 256), 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, n);
   else
-    gelu_kernel<__half, true><<<ew_blocks(n / 8, 256), 256, 0, st>>>((const __half*)x, (const __half*)dy, (__half*)dx, n);
+    launch_k(gelu_kernel<__half, true>, ew_blocks(n / 8, 256), 256, 0, st, (const __half*)x, (const __half*)dy, (__half*)dx, n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;
@@ -192,9 +196,9 @@ extern "C" int bimamba_reduce_rows32(const float* part, void* out, int64_t group
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned nb = ew_blocks(groups * nrows * 8, 256);
-  if (out_dtype == BIMAMBA_F32) reduce_rows32_kernel<float><<<nb, 256, 0, st>>>(part, (float*)out, groups, nparts, nrows, out_ld);
-  else if (out_dtype == BIMAMBA_BF16) reduce_rows32_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(part, (__nv_bfloat16*)out, groups, nparts, nrows, out_ld);
-  else reduce_rows32_kernel<__half><<<nb, 256, 0, st>>>(part, (__half*)out, groups, nparts, nrows, out_ld);
+  if (out_dtype == BIMAMBA_F32) launch_k(reduce_rows32_kernel<float>, nb, 256, 0, st, part, (float*)out, groups, nparts, nrows, out_ld);
+  else if (out_dtype == BIMAMBA_BF16) launch_k(reduce_rows32_kernel<__nv_bfloat16>, nb, 256, 0, st, part, (__nv_bfloat16*)out, groups, nparts, nrows, out_ld);
+  else launch_k(reduce_rows32_kernel<__half>, nb, 256, 0, st, part, (__half*)out, groups, nparts, nrows, out_ld);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;
@@ -214,7 +218,7 @@ extern "C" int bimamba_finalize_param_grads(const float* dA, const float* A, con
   }
   FinalizeArgs a{dA, A, dWxp, dWdt_full, dWo2, dwb, dA_log, dWx, dWdt, dWo, dconv_w, dconv_b, d_inner, d_state, dt_rank, d_model, ndir, d_conv};
   const int total = d_inner * d_state + (dt_rank + 2 * d_state) * d_inner + d_inner * dt_rank + d_model * d_inner + d_inner * (d_conv + 1);
-  finalize_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  launch_k(finalize_kernel, ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;
@@ -227,7 +231,7 @@ extern "C" int bimamba_split3_bf16(const float* src, void* dst, int64_t rows, in
     set_err("split3_bf16: bad arguments");
     return -1;
   }
-  split3_kernel<<<ew_blocks(rows * cols, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(split3_kernel, ew_blocks(rows * cols, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       src, reinterpret_cast<__nv_bfloat16*>(dst), rows, cols, ld_src, ld_dst, block_stride, side);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }

@@ -136,6 +136,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                TOut* __restrict__ C, const float* __restrict__ bias, const TOut* __restrict__ addend, int M, int N,
                int K, int64_t ldc, int block_n,
                int stages, uint32_t idesc, uint32_t tmem_cols, int staged) {
+  pdl_prologue();
   extern __shared__ __align__(1024) unsigned char gsm[];
   __shared__ __align__(8) uint64_t full_bar[kGStagesMax], empty_bar[kGStagesMax], accum_bar;
   __shared__ uint32_t tmem_slot;
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
 gemm_nt_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        TOut* __restrict__ C, const float* __restrict__ bias, const TOut* __restrict__ addend, int M,
                        int N, int K, int64_t ldc, int block_n, uint32_t idesc, uint32_t tmem_cols, uint32_t acc_stride) {
+  pdl_prologue();
   extern __shared__ __align__(1024) unsigned char gsm[];
   __shared__ __align__(8) uint64_t full_bar[kPStages], empty_bar[kPStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -464,6 +466,7 @@ __global__ void __launch_bounds__(kGThreads)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                float* __restrict__ part, int M, int NP, int NQ, int block_q, int kb_per_split, uint32_t idesc,
                uint32_t tmem_cols) {
+  pdl_prologue();
   extern __shared__ __align__(1024) unsigned char gsm[];
   __shared__ __align__(8) uint64_t full_bar[kTNStages], empty_bar[kTNStages], accum_bar;
   __shared__ uint32_t tmem_slot;
@@ -553,6 +556,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant_
 // out = sum over the splits of part[z][q][p], in split order; p_is_row: out is (NP, NQ) row-major, else (NQ, NP).
 __global__ void __launch_bounds__(256)
 tn_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nsplit, int NP, int NQ, int p_is_row) {
+  pdl_prologue();
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const int total = NP * NQ;
   if (idx >= total) return;
@@ -700,7 +704,7 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
 #define GEMM_PLAUNCH(TOUT)                                                                                         \
   do {                                                                                                             \
     cudaFuncSetAttribute(gemm_nt_persist_kernel<TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);   \
-    gemm_nt_persist_kernel<TOUT><<<pgrid, kPThreads, psmem, st>>>(map_a, map_b, reinterpret_cast<TOUT*>(C), bias,   \
+    launch_k(gemm_nt_persist_kernel<TOUT>, pgrid, kPThreads, psmem, st, map_a, map_b, reinterpret_cast<TOUT*>(C), bias,   \
                                                                   reinterpret_cast<const TOUT*>(addend), (int)M, N, K, \
                                                                   ldc, block_n, idesc, pcols, acc_stride);         \
   } while (0)
@@ -717,7 +721,7 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
 #define GEMM_LAUNCH(TOUT)                                                                                          \
   do {                                                                                                             \
     cudaFuncSetAttribute(gemm_nt_kernel<TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-    gemm_nt_kernel<TOUT><<<grid, kGThreads, smem, st>>>(map_a, map_b, reinterpret_cast<TOUT*>(C), bias,             \
+    launch_k(gemm_nt_kernel<TOUT>, grid, kGThreads, smem, st, map_a, map_b, reinterpret_cast<TOUT*>(C), bias,             \
                                                          reinterpret_cast<const TOUT*>(addend), (int)M, N, K, ldc, \
                                                          block_n, stages, idesc, tmem_cols, staged);               \
   } while (0)
@@ -790,8 +794,8 @@ extern "C" int bimamba_gemm_tn(const void* A, int64_t lda, const void* B, int64_
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // per device / context attribute: set on every launch (a process-wide flag would miss the second device)
   cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 6 * kTNBox + 1024);
-  gemm_tn_kernel<<<grid, kGThreads, smem, st>>>(map_p, map_q, part, (int)M, pl.NP, pl.NQ, pl.block_q, pl.per, idesc, tmem_cols);
-  tn_reduce_kernel<<<(unsigned)(((int64_t)N1 * N2 + 255) / 256), 256, 0, st>>>(part, C, pl.nsplit, pl.NP, pl.NQ, pl.p_is_a);
+  launch_k(gemm_tn_kernel, grid, kGThreads, smem, st, map_p, map_q, part, (int)M, pl.NP, pl.NQ, pl.block_q, pl.per, idesc, tmem_cols);
+  launch_k(tn_reduce_kernel, (unsigned)(((int64_t)N1 * N2 + 255) / 256), 256, 0, st, part, C, pl.nsplit, pl.NP, pl.NQ, pl.p_is_a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

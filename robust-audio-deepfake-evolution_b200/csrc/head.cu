@@ -27,6 +27,7 @@ head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const 
                 const float* __restrict__ w_att, const float* __restrict__ b_att, const float* __restrict__ w_cls,
                 const float* __restrict__ b_cls, float* __restrict__ features, float* __restrict__ logits, int L, int C,
                 int ncls, float eps) {
+  pdl_prologue();
   __shared__ float s_m[kHeadWarps], s_l[kHeadWarps];
   __shared__ float s_acc[kHeadWarps][32 * NPL];
   __shared__ float s_feat[32 * NPL];
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ w_att, const float* __restrict__ b_att, const float* __restrict__ dfeat,
                 T* __restrict__ dx, float* __restrict__ part /* (batch, 4, C) */, int L, int C, float eps) {
+  pdl_prologue();
   __shared__ float s_m[kHeadWarps], s_l[kHeadWarps];
   __shared__ float s_acc[kHeadWarps][32 * NPL];
   __shared__ float s_db[kHeadWarps];
@@ -274,9 +276,9 @@ static void launch_head(const void* x, const float* gamma, const float* beta, co
                         int ncls, float eps, cudaStream_t st) {
   const T* xp = reinterpret_cast<const T*>(x);
   if (C <= 160)
-    head_fwd_kernel<T, 5><<<batch, kHeadThreads, 0, st>>>(xp, gamma, beta, w_att, b_att, w_cls, b_cls, features, logits, L, C, ncls, eps);
+    launch_k(head_fwd_kernel<T, 5>, batch, kHeadThreads, 0, st, xp, gamma, beta, w_att, b_att, w_cls, b_cls, features, logits, L, C, ncls, eps);
   else
-    head_fwd_kernel<T, 8><<<batch, kHeadThreads, 0, st>>>(xp, gamma, beta, w_att, b_att, w_cls, b_cls, features, logits, L, C, ncls, eps);
+    launch_k(head_fwd_kernel<T, 8>, batch, kHeadThreads, 0, st, xp, gamma, beta, w_att, b_att, w_cls, b_cls, features, logits, L, C, ncls, eps);
 }
 
 }  // namespace bimamba
@@ -311,10 +313,10 @@ extern "C" int bimamba_head_pool_bwd(const void* x, const float* gamma, const fl
 #define HEAD_BWD(T)                                                                                                         \
   do {                                                                                                                      \
     if (channels <= 160)                                                                                                    \
-      head_bwd_kernel<T, 5><<<batch, kHeadThreads, 0, st>>>((const T*)x, gamma, beta, w_att, b_att, dfeatures, (T*)dx, part, \
+      launch_k(head_bwd_kernel<T, 5>, batch, kHeadThreads, 0, st, (const T*)x, gamma, beta, w_att, b_att, dfeatures, (T*)dx, part, \
                                                             seqlen, channels, eps);                                         \
     else                                                                                                                    \
-      head_bwd_kernel<T, 8><<<batch, kHeadThreads, 0, st>>>((const T*)x, gamma, beta, w_att, b_att, dfeatures, (T*)dx, part, \
+      launch_k(head_bwd_kernel<T, 8>, batch, kHeadThreads, 0, st, (const T*)x, gamma, beta, w_att, b_att, dfeatures, (T*)dx, part, \
                                                             seqlen, channels, eps);                                         \
   } while (0)
   if (dtype == BIMAMBA_F32) HEAD_BWD(float);

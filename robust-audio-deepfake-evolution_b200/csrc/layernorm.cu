@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(kLnThreads)
 ln_fwd_kernel(const Tin* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               Tout* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int C,
               float eps) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(kLnThreads)
 ln_bwd_kernel(const Tin* __restrict__ x, const Tg* __restrict__ dy, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, Tin* __restrict__ dx,
               float* __restrict__ part /* (gridDim.x, 2, C) */, int64_t rows, int C) {
+  pdl_prologue();
   constexpr bool kWide = NPL > 8;     // wide rows: the warps add into one [2][C] buffer in turn (fixed order)
   __shared__ float sm[kWide ? 1 : kLnWarps][2][32 * NPL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -149,9 +151,9 @@ static void launch_ln_fwd(const void* x, const float* gamma, const float* beta, 
   const unsigned blocks = (unsigned)((rows + kLnWarps - 1) / kLnWarps);
   const Tin* xp = reinterpret_cast<const Tin*>(x);
   Tout* yp = reinterpret_cast<Tout*>(y);
-  if (C <= 160) ln_fwd_kernel<Tin, Tout, 5><<<blocks, kLnThreads, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, C, eps);
-  else if (C <= 256) ln_fwd_kernel<Tin, Tout, 8><<<blocks, kLnThreads, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, C, eps);
-  else ln_fwd_kernel<Tin, Tout, kLnMaxPerLane><<<blocks, kLnThreads, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, C, eps);
+  if (C <= 160) launch_k(ln_fwd_kernel<Tin, Tout, 5>, blocks, kLnThreads, 0, st, xp, gamma, beta, yp, mean, rstd, rows, C, eps);
+  else if (C <= 256) launch_k(ln_fwd_kernel<Tin, Tout, 8>, blocks, kLnThreads, 0, st, xp, gamma, beta, yp, mean, rstd, rows, C, eps);
+  else launch_k(ln_fwd_kernel<Tin, Tout, kLnMaxPerLane>, blocks, kLnThreads, 0, st, xp, gamma, beta, yp, mean, rstd, rows, C, eps);
 }
 
 template <typename Tin, typename Tg>
@@ -161,9 +163,9 @@ static void launch_ln_bwd(const void* x, const void* dy, const float* gamma, con
   const Tin* xp = reinterpret_cast<const Tin*>(x);
   const Tg* gp = reinterpret_cast<const Tg*>(dy);
   Tin* dxp = reinterpret_cast<Tin*>(dx);
-  if (C <= 160) ln_bwd_kernel<Tin, Tg, 5><<<blocks, kLnThreads, 0, st>>>(xp, gp, gamma, mean, rstd, dxp, part, rows, C);
-  else if (C <= 256) ln_bwd_kernel<Tin, Tg, 8><<<blocks, kLnThreads, 0, st>>>(xp, gp, gamma, mean, rstd, dxp, part, rows, C);
-  else ln_bwd_kernel<Tin, Tg, kLnMaxPerLane><<<blocks, kLnThreads, 0, st>>>(xp, gp, gamma, mean, rstd, dxp, part, rows, C);
+  if (C <= 160) launch_k(ln_bwd_kernel<Tin, Tg, 5>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, dxp, part, rows, C);
+  else if (C <= 256) launch_k(ln_bwd_kernel<Tin, Tg, 8>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, dxp, part, rows, C);
+  else launch_k(ln_bwd_kernel<Tin, Tg, kLnMaxPerLane>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, dxp, part, rows, C);
 }
 
 }  // namespace bimamba

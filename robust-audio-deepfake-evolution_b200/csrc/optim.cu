@@ -15,7 +15,8 @@ namespace bimamba {
 constexpr int kAdamThreads = 256;
 constexpr int kAdamChunk = 4096;   // elements per CTA
 
-__global__ void adamw_tick_kernel(float* state) { state[0] += 1.f; }
+__global__ void adamw_tick_kernel(float* state) {
+  pdl_prologue(); state[0] += 1.f; }
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps,
                                           float decay, float inv_bc1, float inv_sqrt_bc2) {
@@ -29,6 +30,7 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(kAdamThreads)
 adamw_kernel(const bimamba_adamw_tensor* __restrict__ tab, const int2* __restrict__ blocks,
              const float* __restrict__ hyper, const float* __restrict__ state) {
+  pdl_prologue();
   const int2 bm = blocks[blockIdx.x];
   const bimamba_adamw_tensor t = tab[bm.x];
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
@@ -73,8 +75,8 @@ extern "C" int bimamba_adamw_step(const bimamba_adamw_tensor* table, const int32
   if (nblocks == 0) return 0;
   if (!table || !block_map || !hyper || !state || nblocks < 0) { set_err("adamw: null operand"); return -1; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  adamw_tick_kernel<<<1, 1, 0, st>>>(state);
-  adamw_kernel<<<nblocks, kAdamThreads, 0, st>>>(table, reinterpret_cast<const int2*>(block_map), hyper, state);
+  launch_k(adamw_tick_kernel, 1, 1, 0, st, state);
+  launch_k(adamw_kernel, nblocks, kAdamThreads, 0, st, table, reinterpret_cast<const int2*>(block_map), hyper, state);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

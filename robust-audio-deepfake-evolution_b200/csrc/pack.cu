@@ -24,6 +24,7 @@ struct PackArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
+  pdl_prologue();
   const int dm = a.dm, D = a.D, N = a.N, R = a.R;
   const int64_t n_wi = (int64_t)2 * D * dm, n_xp = (int64_t)kXW * D, n_wo2 = (int64_t)dm * a.ndir * D,
                 n_wot = (int64_t)D * dm, n_wdt = (int64_t)BIMAMBA_MAX_DT_RANK * D, n_a = (int64_t)D * N;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 cast_transpose_kernel(const float* __restrict__ src, T* __restrict__ dst, T* __restrict__ dstT, int rows, int cols) {
+  pdl_prologue();
   const int64_t n = (int64_t)rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * 256) {
     if (i < n) {
@@ -114,9 +116,9 @@ extern "C" int bimamba_pack_weights(const float* W_in, const float* W_x, const f
                         (int64_t)d_inner * d_model + (int64_t)BIMAMBA_MAX_DT_RANK * d_inner + (int64_t)d_inner * d_state;
   const unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == BIMAMBA_F32) pack_kernel<float><<<blocks, 256, 0, st>>>(a);
-  else if (dtype == BIMAMBA_BF16) pack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
-  else pack_kernel<__half><<<blocks, 256, 0, st>>>(a);
+  if (dtype == BIMAMBA_F32) launch_k(pack_kernel<float>, blocks, 256, 0, st, a);
+  else if (dtype == BIMAMBA_BF16) launch_k(pack_kernel<__nv_bfloat16>, blocks, 256, 0, st, a);
+  else launch_k(pack_kernel<__half>, blocks, 256, 0, st, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;
@@ -130,9 +132,9 @@ extern "C" int bimamba_cast_transpose(const float* src, void* dst, void* dstT, i
   const int64_t total = 2 * (int64_t)rows * cols;
   const unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == BIMAMBA_F32) cast_transpose_kernel<float><<<blocks, 256, 0, st>>>(src, reinterpret_cast<float*>(dst), reinterpret_cast<float*>(dstT), rows, cols);
-  else if (dtype == BIMAMBA_BF16) cast_transpose_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<__nv_bfloat16*>(dstT), rows, cols);
-  else cast_transpose_kernel<__half><<<blocks, 256, 0, st>>>(src, reinterpret_cast<__half*>(dst), reinterpret_cast<__half*>(dstT), rows, cols);
+  if (dtype == BIMAMBA_F32) launch_k(cast_transpose_kernel<float>, blocks, 256, 0, st, src, reinterpret_cast<float*>(dst), reinterpret_cast<float*>(dstT), rows, cols);
+  else if (dtype == BIMAMBA_BF16) launch_k(cast_transpose_kernel<__nv_bfloat16>, blocks, 256, 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<__nv_bfloat16*>(dstT), rows, cols);
+  else launch_k(cast_transpose_kernel<__half>, blocks, 256, 0, st, src, reinterpret_cast<__half*>(dst), reinterpret_cast<__half*>(dstT), rows, cols);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

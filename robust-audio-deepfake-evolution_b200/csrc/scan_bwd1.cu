@@ -64,6 +64,7 @@ struct LaneSmem {
 
 template <typename T, int kMode, int kNW, int kSplit>
 __global__ void __launch_bounds__(32 * kNW, kSplit == 2 ? 16 / kNW : 1) scan_bwd_lane_kernel(const bimamba_scan_desc p) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = LaneSmem<T, kNW, kSplit>;
   constexpr bool expl = kMode == 0;
@@ -475,7 +476,7 @@ static void launch_lane3(const bimamba_scan_desc* d, cudaStream_t st) {
     cudaFuncSetAttribute(scan_bwd_lane_kernel<T, kMode, kNW, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   constexpr int G = 32 * kNW / kSplit;
   dim3 grid((d->dim + G - 1) / G, d->ndir, d->batch);
-  scan_bwd_lane_kernel<T, kMode, kNW, kSplit><<<grid, 32 * kNW, smem, st>>>(*d);
+  launch_k(scan_bwd_lane_kernel<T, kMode, kNW, kSplit>, grid, 32 * kNW, smem, st, *d);
 }
 
 // group_channels == 32 (checked by the caller).  One warp per CTA, one lane per channel: the two-lanes-per-channel

@@ -35,6 +35,7 @@ constexpr int kFwdMaxThreads = 128;
 // kMode: 0 = delta given; 1 = fused dt projection with dt_rank <= 12; 2 = dt_rank <= 16.
 template <typename T, int kMode, bool kGate>
 __global__ void __launch_bounds__(kFwdMaxThreads) scan_fwd_kernel(const bimamba_scan_desc p) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool expl = kMode == 0;
   constexpr int R4 = kMode == 1 ? 3 : 4;
@@ -204,7 +205,7 @@ static void launch_fwd2(const bimamba_scan_desc* d, cudaStream_t st) {
   dim3 grid((d->dim + G - 1) / G, d->ndir, d->batch);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(scan_fwd_kernel<T, kMode, kGate>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  scan_fwd_kernel<T, kMode, kGate><<<grid, G, smem, st>>>(*d);
+  launch_k(scan_fwd_kernel<T, kMode, kGate>, grid, G, smem, st, *d);
 }
 
 template <typename T>

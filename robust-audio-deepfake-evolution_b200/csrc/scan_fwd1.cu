@@ -12,6 +12,7 @@ constexpr int kF1G = 32;
 
 template <typename T, int kMode, bool kGate>
 __global__ void __launch_bounds__(kF1G) scan_fwd_warp_kernel(const bimamba_scan_desc p) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool expl = kMode == 0;
   constexpr int R4 = kMode == 1 ? 3 : 4;
@@ -212,7 +213,7 @@ template <typename T, int kMode, bool kGate>
 static void launch_warp2(const bimamba_scan_desc* d, cudaStream_t st) {
   const size_t smem = (size_t)kT * kXW * 4 + (size_t)2 * kT * kXW * sizeof(T) + (size_t)2 * 3 * kT * kF1G * sizeof(T);
   dim3 grid((d->dim + kF1G - 1) / kF1G, d->ndir, d->batch);
-  scan_fwd_warp_kernel<T, kMode, kGate><<<grid, kF1G, smem, st>>>(*d);
+  launch_k(scan_fwd_warp_kernel<T, kMode, kGate>, grid, kF1G, smem, st, *d);
 }
 
 template <typename T>
