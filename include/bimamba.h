@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 6
+#define BIMAMBA_ABI_VERSION 7
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -231,11 +231,13 @@ int bimamba_layernorm_fwd(const void* x, const float* gamma, const float* beta, 
                           bimamba_stream_t stream);
 
 /* dx (x's dtype) and per-CTA partials dgb_part (nblocks, 2, channels) fp32 = [dgamma | dbeta] with
- * nblocks = bimamba_layernorm_bwd_blocks(rows); reduce with bimamba_reduce_partials.  channels <= 1024. */
+ * nblocks = bimamba_layernorm_bwd_blocks(rows); reduce with bimamba_reduce_partials.  channels <= 1024.
+ * dx_addend (optional, x's dtype, same layout as dx): added to dx - the gradient of a residual branch that bypasses the
+ * norm (out = f(LN(x)) + x, DualStreamSEMamba.py:471-485), so autograd needs no separate add. */
 int bimamba_layernorm_bwd_blocks(int64_t rows);
 int bimamba_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean,
-                          const float* rstd, void* dx, float* dgb_part, int64_t rows, int channels,
-                          int x_dtype, int dy_dtype, bimamba_stream_t stream);
+                          const float* rstd, const void* dx_addend, void* dx, float* dgb_part, int64_t rows,
+                          int channels, int x_dtype, int dy_dtype, bimamba_stream_t stream);
 
 /* C[M, N] = A[M, K] . B[N, K]^T (+ bias[N]) (+ addend[M, N]) with bf16 / fp16 operands (row-major, K contiguous, row strides
  * lda / ldb in elements, multiples of 8, 16-byte aligned bases) and fp32 accumulation on the tcgen05 tensor

@@ -15,7 +15,7 @@ F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
 FLAG_DTR_PADDED = 2
 FLAG_SILU = 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 CHUNK = 16
 
 EXPORTS = (
@@ -97,7 +97,7 @@ def load() -> C.CDLL:
         lib.bimamba_layernorm_bwd_blocks.restype = i32
         lib.bimamba_layernorm_bwd_blocks.argtypes = [i64]
         lib.bimamba_layernorm_bwd.restype = i32
-        lib.bimamba_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]
+        lib.bimamba_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]
         lib.bimamba_gemm_nt_block_n.restype = i32
         lib.bimamba_gemm_nt_block_n.argtypes = [i32]
         lib.bimamba_pack_weights.restype = i32

@@ -62,8 +62,8 @@ ln_fwd_kernel(const Tin* __restrict__ x, const float* __restrict__ gamma, const 
 template <typename Tin, typename Tg, int NPL>
 __global__ void __launch_bounds__(kLnThreads)
 ln_bwd_kernel(const Tin* __restrict__ x, const Tg* __restrict__ dy, const float* __restrict__ gamma,
-              const float* __restrict__ mean, const float* __restrict__ rstd, Tin* __restrict__ dx,
-              float* __restrict__ part /* (gridDim.x, 2, C) */, int64_t rows, int C) {
+              const float* __restrict__ mean, const float* __restrict__ rstd, const Tin* __restrict__ addend,
+              Tin* __restrict__ dx, float* __restrict__ part /* (gridDim.x, 2, C) */, int64_t rows, int C) {
   pdl_prologue();
   constexpr bool kWide = NPL > 8;     // wide rows: the warps add into one [2][C] buffer in turn (fixed order)
   __shared__ float sm[kWide ? 1 : kLnWarps][2][32 * NPL];
@@ -100,10 +100,11 @@ ln_bwd_kernel(const Tin* __restrict__ x, const Tg* __restrict__ dy, const float*
     s1 = warp_sum(s1) / C;
     s2 = warp_sum(s2) / C;
     Tin* dr = dx + row * C;
+    const Tin* ar = addend ? addend + row * C : nullptr;    // gradient of the residual branch that bypasses the norm
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
       const int c = lane + 32 * i;
-      if (c < C) dr[c] = from_f<Tin>(rs * (dxh[i] - s1 - xh[i] * s2));
+      if (c < C) dr[c] = from_f<Tin>(rs * (dxh[i] - s1 - xh[i] * s2) + (ar ? to_f(ar[c]) : 0.f));
     }
   }
   if constexpr (kWide) {
@@ -158,14 +159,15 @@ static void launch_ln_fwd(const void* x, const float* gamma, const float* beta, 
 
 template <typename Tin, typename Tg>
 static void launch_ln_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd,
-                          void* dx, float* part, int64_t rows, int C, cudaStream_t st) {
+                          const void* addend, void* dx, float* part, int64_t rows, int C, cudaStream_t st) {
   const unsigned blocks = (unsigned)ln_blocks(rows);
   const Tin* xp = reinterpret_cast<const Tin*>(x);
   const Tg* gp = reinterpret_cast<const Tg*>(dy);
   Tin* dxp = reinterpret_cast<Tin*>(dx);
-  if (C <= 160) launch_k(ln_bwd_kernel<Tin, Tg, 5>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, dxp, part, rows, C);
-  else if (C <= 256) launch_k(ln_bwd_kernel<Tin, Tg, 8>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, dxp, part, rows, C);
-  else launch_k(ln_bwd_kernel<Tin, Tg, kLnMaxPerLane>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, dxp, part, rows, C);
+  const Tin* ap = reinterpret_cast<const Tin*>(addend);
+  if (C <= 160) launch_k(ln_bwd_kernel<Tin, Tg, 5>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, ap, dxp, part, rows, C);
+  else if (C <= 256) launch_k(ln_bwd_kernel<Tin, Tg, 8>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, ap, dxp, part, rows, C);
+  else launch_k(ln_bwd_kernel<Tin, Tg, kLnMaxPerLane>, blocks, kLnThreads, 0, st, xp, gp, gamma, mean, rstd, ap, dxp, part, rows, C);
 }
 
 }  // namespace bimamba
@@ -200,13 +202,13 @@ extern "C" int bimamba_layernorm_fwd(const void* x, const float* gamma, const fl
 extern "C" int bimamba_layernorm_bwd_blocks(int64_t rows) { return ln_blocks(rows); }
 
 extern "C" int bimamba_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean,
-                                     const float* rstd, void* dx, float* dgb_part, int64_t rows, int channels,
-                                     int x_dtype, int dy_dtype, bimamba_stream_t stream) {
+                                     const float* rstd, const void* dx_addend, void* dx, float* dgb_part, int64_t rows,
+                                     int channels, int x_dtype, int dy_dtype, bimamba_stream_t stream) {
   if (rows == 0) return 0;
   if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgb_part) { set_err("layernorm bwd: null operand"); return -1; }
   if (channels < 1 || channels > 32 * kLnMaxPerLane || rows < 0) { set_err("layernorm backward: channels must be 1..1024"); return -3; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  LN_DISPATCH2(x_dtype, dy_dtype, (launch_ln_bwd<T1, T2>(x, dy, gamma, mean, rstd, dx, dgb_part, rows, channels, st)));
+  LN_DISPATCH2(x_dtype, dy_dtype, (launch_ln_bwd<T1, T2>(x, dy, gamma, mean, rstd, dx_addend, dx, dgb_part, rows, channels, st)));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

@@ -27,8 +27,9 @@ class PN_BiMambas_Encoder(nn.Module):
         )
 
     def forward(self, x):
-        residual = x
-        x_norm = layer_norm_fn(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)               # :472
+        # :471-472; the residual branch leaves the LayerNorm Function as its second output, so its gradient is added to dx
+        # inside the LayerNorm backward kernel (no separate autograd add)
+        x_norm, residual = layer_norm_fn(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, with_residual=True)
         mamba_out = self.mamba.forward_bidirectional(x_norm)                                         # :473-481 in one fused pass
         mamba_out = layer_norm_fn(mamba_out, self.norm2.weight, self.norm2.bias, self.norm2.eps)    # :482
         if isinstance(self.feed_forward[1], nn.GELU) and self.feed_forward[1].approximate == "none":

@@ -634,7 +634,7 @@ class LayerNormFn(torch.autograd.Function):
     reads); statistics in fp32.  x (..., C) fp32 / bf16 / fp16."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, out_dtype, needs_bwd=True):
+    def forward(ctx, x, weight, bias, eps, out_dtype, needs_bwd=True, with_residual=False):
         _require_cuda(x, weight, bias)
         lib = _lib.load()
         C_ = x.shape[-1]
@@ -653,14 +653,25 @@ class LayerNormFn(torch.autograd.Function):
         if needs_bwd:
             ctx.save_for_backward(x2, w32, mean, rstd)
             ctx.meta = (x.shape, weight.dtype, bias.dtype)
+        if with_residual:
+            # second output = x itself (the residual branch): its gradient comes back into backward() and is added to dx
+            # inside the LayerNorm backward kernel instead of by a separate autograd add
+            return y.view(x.shape), x
         return y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dres=None):
         x2, w32, mean, rstd = ctx.saved_tensors
         shape, wdt, bdt = ctx.meta
         lib = _lib.load()
         rows, C_ = x2.shape
+        if dy is None:                       # only the residual branch was used
+            return (dres, None, None, None, None, None, None)
+        add2 = None
+        if dres is not None:
+            add2 = dres.reshape(rows, C_)
+            if add2.dtype != x2.dtype or not add2.is_contiguous():
+                add2 = add2.to(x2.dtype).contiguous()
         g2 = dy.reshape(rows, C_)
         if g2.dtype not in _DT or (g2.dtype != x2.dtype and g2.dtype != torch.float32 and x2.dtype != torch.float32):
             g2 = g2.to(x2.dtype)
@@ -669,7 +680,7 @@ class LayerNormFn(torch.autograd.Function):
         nb = lib.bimamba_layernorm_bwd_blocks(rows)
         part = torch.empty((nb, 2, C_), device=x2.device, dtype=torch.float32)
         with _timed("ln_bwd"):
-            _lib.check(lib.bimamba_layernorm_bwd(_ptr(x2), _ptr(g2), _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(dx),
+            _lib.check(lib.bimamba_layernorm_bwd(_ptr(x2), _ptr(g2), _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(add2), _ptr(dx),
                                                  _ptr(part), rows, C_, _dt(x2), _dt(g2), _stream()),
                        "bimamba_layernorm_bwd")
         dgb = torch.empty((2, C_), device=x2.device, dtype=torch.float32)
@@ -677,7 +688,7 @@ class LayerNormFn(torch.autograd.Function):
             dgb.zero_()
         else:
             reduce_raw(part, dgb, groups=1, rows=nb, cols=2 * C_, part_gs=0, row_stride=2 * C_, out_gs=0)
-        return dx.view(shape), dgb[0].to(wdt), dgb[1].to(bdt), None, None, None
+        return dx.view(shape), dgb[0].to(wdt), dgb[1].to(bdt), None, None, None, None
 
 
 def head_fwd(x, norm_w, norm_b, att_w, att_b, cls_w, cls_b, eps=1e-5):
@@ -798,11 +809,13 @@ def linear_fn(x, W, b=None, addend=None, compute_dtype=None, out_dtype=None):
     return LinearFn.apply(x, W, b, addend, compute_dtype, out_dtype, _wants_grad(x, W, b, addend))
 
 
-def layer_norm_fn(x, weight, bias, eps=1e-5, out_dtype=None):
-    """LayerNorm over the last axis; out_dtype defaults to the autocast dtype when autocast is on, else x.dtype."""
+def layer_norm_fn(x, weight, bias, eps=1e-5, out_dtype=None, with_residual=False):
+    """LayerNorm over the last axis; out_dtype defaults to the autocast dtype when autocast is on, else x.dtype.
+    with_residual=True returns (LayerNorm(x), x): use the second output as the residual branch of a pre-norm layer
+    (out = f(LN(x)) + x) and its gradient is added inside the LayerNorm backward kernel."""
     if out_dtype is None:
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
-    return LayerNormFn.apply(x, weight, bias, eps, out_dtype, _wants_grad(x, weight, bias))
+    return LayerNormFn.apply(x, weight, bias, eps, out_dtype, _wants_grad(x, weight, bias), with_residual)
 
 
 # ----------------------------------------------------------------------------------------
