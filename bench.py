@@ -374,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
     def fwd_loss(x):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = model.forward_features(x)
-        return out.float().square().mean()
+        return bm.ops.mean_square_loss(out)          # mean(out^2) in fp32 (one launch forward, one backward)
 
     use_graph = not args.no_graph
     if use_graph and world == 1:

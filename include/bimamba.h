@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 7
+#define BIMAMBA_ABI_VERSION 8
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -279,6 +279,17 @@ int bimamba_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dty
  * block_stride = rows * ld_dst they extend the row axis bimamba_gemm_tn contracts over. */
 int bimamba_split3_bf16(const float* src, void* dst, int64_t rows, int cols, int64_t ld_src, int64_t ld_dst,
                         int64_t block_stride, int side, bimamba_stream_t stream);
+
+/* dst = cast(src) over n contiguous elements (16-byte aligned bases): the dtype changes at the edges of a layer's
+ * 16-bit region (autocast of src/main.py:1049). */
+int bimamba_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, bimamba_stream_t stream);
+
+/* Mean-of-squares loss pieces (the benchmark's synthetic loss on the backend output): per-CTA partial sums of x^2
+ * (each multiplied by `scale`, e.g. 1/n; nslices = bimamba_sumsq_slices(n) floats; finish with bimamba_reduce_partials) and dx = g[0] * scale * x with g on
+ * the device. */
+int bimamba_sumsq_slices(int64_t n);
+int bimamba_sumsq(const void* x, float* part, int64_t n, float scale, int dtype, bimamba_stream_t stream);
+int bimamba_scale_by(const void* x, const float* g, void* dx, int64_t n, float scale, int dtype, bimamba_stream_t stream);
 
 /* Channel-group sum of the backward scan's [dB | dC] partial rows, written into the first 32 columns of a row matrix:
  *   out[(g * nrows + r) * out_ld + c] = sum_{i < nparts} part[((g * nparts + i) * nrows + r) * 32 + c],  c < 32

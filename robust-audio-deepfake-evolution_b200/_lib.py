@@ -15,7 +15,7 @@ F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
 FLAG_DTR_PADDED = 2
 FLAG_SILU = 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 CHUNK = 16
 
 EXPORTS = (
@@ -25,7 +25,7 @@ EXPORTS = (
     "bimamba_reduce_partials", "bimamba_layernorm_fwd", "bimamba_layernorm_bwd_blocks", "bimamba_layernorm_bwd",
     "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_gemm_tn_splits", "bimamba_gemm_tn", "bimamba_adamw_chunk", "bimamba_adamw_step", "bimamba_head_fwd", "bimamba_colsum_slices", "bimamba_colsum", "bimamba_pack_weights", "bimamba_cast_transpose",
     "bimamba_gelu_fwd", "bimamba_gelu_bwd", "bimamba_reduce_rows32", "bimamba_finalize_param_grads", "bimamba_head_pool_bwd", "bimamba_set_tuning", "bimamba_get_tuning",
-    "bimamba_scan_fwd_workspace_bytes", "bimamba_scan_bwd_workspace_bytes", "bimamba_split3_bf16",
+    "bimamba_scan_fwd_workspace_bytes", "bimamba_scan_bwd_workspace_bytes", "bimamba_split3_bf16", "bimamba_cast", "bimamba_sumsq_slices", "bimamba_sumsq", "bimamba_scale_by",
 )
 
 
@@ -142,6 +142,14 @@ def load() -> C.CDLL:
         lib.bimamba_scan_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32]
         lib.bimamba_split3_bf16.restype = i32
         lib.bimamba_split3_bf16.argtypes = [vp, vp, i64, i32, i64, i64, i64, i32, vp]
+        lib.bimamba_cast.restype = i32
+        lib.bimamba_cast.argtypes = [vp, vp, i64, i32, i32, vp]
+        lib.bimamba_sumsq_slices.restype = i32
+        lib.bimamba_sumsq_slices.argtypes = [i64]
+        lib.bimamba_sumsq.restype = i32
+        lib.bimamba_sumsq.argtypes = [vp, vp, i64, C.c_float, i32, vp]
+        lib.bimamba_scale_by.restype = i32
+        lib.bimamba_scale_by.argtypes = [vp, vp, vp, i64, C.c_float, i32, vp]
         got = lib.bimamba_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError(f"libbimamba ABI {got} != expected {ABI_VERSION}; rebuild the library")

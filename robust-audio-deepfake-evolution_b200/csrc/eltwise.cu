@@ -92,6 +92,70 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ s
   }
 }
 
+// dst = cast(src): the dtype changes at the edges of the 16-bit region of a layer (fp32 residual-stream gradient ->
+// bf16 GEMM operand), 8 elements per thread.
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  pdl_prologue();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      TS v[8];
+      TD o[8];
+      if constexpr (sizeof(TS) == 4) {
+        *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(src + i));
+        *reinterpret_cast<uint4*>(v + 4) = __ldg(reinterpret_cast<const uint4*>(src + i + 4));
+      } else {
+        *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(src + i));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = from_f<TD>(to_f(v[k]));
+      if constexpr (sizeof(TD) == 4) {
+        *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(dst + i + 4) = *reinterpret_cast<const uint4*>(o + 4);
+      } else {
+        *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(o);
+      }
+    } else {
+      for (int64_t j = i; j < n; ++j) dst[j] = from_f<TD>(to_f(src[j]));
+    }
+  }
+}
+
+// Mean of squares (the benchmark's / a regression loss): stage 1 = per-CTA fp32 partial sums in fixed order, finished
+// by bimamba_reduce_partials; backward dx = g * 2 x / n with g read from device memory (no host sync).
+template <typename T>
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, float* __restrict__ part, int64_t n, float scale) {
+  pdl_prologue();
+  __shared__ float sm[8];
+  float s = 0.f;
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const float v = to_f(x[i]);
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    part[blockIdx.x] = t * scale;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_by_kernel(const T* __restrict__ x, const float* __restrict__ g, T* __restrict__ dx,
+                                                       int64_t n, float scale) {
+  pdl_prologue();
+  const float f = __ldg(g) * scale;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = from_f<T>(to_f(x[i]) * f);
+}
+
 struct FinalizeArgs {
   const float* dA;       // (D, N)       sum_t dh a h delta
   const float* A;        // (D, N)       -exp(A_log)
@@ -233,6 +297,60 @@ extern "C" int bimamba_split3_bf16(const float* src, void* dst, int64_t rows, in
   }
   launch_k(split3_kernel, ew_blocks(rows * cols, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       src, reinterpret_cast<__nv_bfloat16*>(dst), rows, cols, ld_src, ld_dst, block_stride, side);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+#define EW_DISPATCH1(DT, CALL)                                                     \
+  do {                                                                             \
+    if (DT == BIMAMBA_F32) { using T = float; CALL; }                               \
+    else if (DT == BIMAMBA_BF16) { using T = __nv_bfloat16; CALL; }                 \
+    else { using T = __half; CALL; }                                               \
+  } while (0)
+
+extern "C" int bimamba_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, bimamba_stream_t stream) {
+  if (n == 0) return 0;
+  if (!src || !dst || n < 0 || src_dtype < 0 || src_dtype > 2 || dst_dtype < 0 || dst_dtype > 2) { set_err("cast: bad arguments"); return -1; }
+  if (!aligned16(src) || !aligned16(dst)) { set_err("cast: operands must be 16-byte aligned"); return -10; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned nb = ew_blocks((n + 7) / 8, 256);
+#define CAST2(TS)                                                                                                    \
+  do {                                                                                                               \
+    if (dst_dtype == BIMAMBA_F32) launch_k(cast_kernel<TS, float>, nb, 256, 0, st, (const TS*)src, (float*)dst, n);   \
+    else if (dst_dtype == BIMAMBA_BF16) launch_k(cast_kernel<TS, __nv_bfloat16>, nb, 256, 0, st, (const TS*)src, (__nv_bfloat16*)dst, n); \
+    else launch_k(cast_kernel<TS, __half>, nb, 256, 0, st, (const TS*)src, (__half*)dst, n);                          \
+  } while (0)
+  if (src_dtype == BIMAMBA_F32) CAST2(float);
+  else if (src_dtype == BIMAMBA_BF16) CAST2(__nv_bfloat16);
+  else CAST2(__half);
+#undef CAST2
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+extern "C" int bimamba_sumsq_slices(int64_t n) {
+  int64_t b = (n + 4095) / 4096;
+  return (int)(b < 1 ? 1 : (b > 148 * 4 ? 148 * 4 : b));
+}
+
+extern "C" int bimamba_sumsq(const void* x, float* part, int64_t n, float scale, int dtype, bimamba_stream_t stream) {
+  if (!x || !part || n < 1 || dtype < 0 || dtype > 2) { set_err("sumsq: bad arguments"); return -1; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned nb = (unsigned)bimamba_sumsq_slices(n);
+  EW_DISPATCH1(dtype, (launch_k(sumsq_kernel<T>, nb, 256, 0, st, (const T*)x, part, n, scale)));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+extern "C" int bimamba_scale_by(const void* x, const float* g, void* dx, int64_t n, float scale, int dtype,
+                                bimamba_stream_t stream) {
+  if (n == 0) return 0;
+  if (!x || !g || !dx || n < 0 || dtype < 0 || dtype > 2) { set_err("scale_by: bad arguments"); return -1; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  EW_DISPATCH1(dtype, (launch_k(scale_by_kernel<T>, ew_blocks(n, 1024), 256, 0, st, (const T*)x, g, (T*)dx, n, scale)));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return (int)e; }
   return 0;

@@ -548,6 +548,55 @@ def colsum(x2: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def cast(t: torch.Tensor, dtype) -> torch.Tensor:
+    """t.to(dtype) on this repository's kernel (contiguous result); a no-op when the dtype already matches."""
+    if t.dtype == dtype:
+        return t
+    if t.dtype not in _DT or dtype not in _DT or not t.is_cuda or not t.is_contiguous() or t.data_ptr() % 16:
+        return t.to(dtype)
+    lib = _lib.load()
+    out = torch.empty(t.shape, device=t.device, dtype=dtype)
+    with _timed("cast"):
+        _lib.check(lib.bimamba_cast(_ptr(t), _ptr(out), t.numel(), _dt(t), _DT[dtype], _stream()), "bimamba_cast")
+    return out
+
+
+class MeanSquareFn(torch.autograd.Function):
+    """loss = mean(x^2) in fp32 (the benchmark's synthetic loss on the backend output): one partial-sum launch + the
+    fixed-order reduction forward, one launch backward; no host synchronisation."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        lib = _lib.load()
+        xc = x.detach().contiguous()
+        n = xc.numel()
+        nsl = lib.bimamba_sumsq_slices(n)
+        part = torch.empty((nsl,), device=x.device, dtype=torch.float32)
+        with _timed("loss"):
+            _lib.check(lib.bimamba_sumsq(_ptr(xc), _ptr(part), n, 1.0 / n, _dt(xc), _stream()), "bimamba_sumsq")
+        out = torch.empty((1,), device=x.device, dtype=torch.float32)
+        reduce_raw(part, out, groups=1, rows=nsl, cols=1, part_gs=0, row_stride=1, out_gs=0)
+        ctx.save_for_backward(xc)
+        ctx.xshape = x.shape
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        lib = _lib.load()
+        n = xc.numel()
+        dx = torch.empty_like(xc)
+        g32 = g.detach().to(torch.float32).reshape(1).contiguous()
+        with _timed("loss"):
+            _lib.check(lib.bimamba_scale_by(_ptr(xc), _ptr(g32), _ptr(dx), n, 2.0 / n, _dt(xc), _stream()), "bimamba_scale_by")
+        return dx.view(ctx.xshape)
+
+
+def mean_square_loss(x: torch.Tensor) -> torch.Tensor:
+    return MeanSquareFn.apply(x)
+
+
 def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
     """Exact (erf) GELU of a contiguous tensor, this repository's kernel (DualStreamSEMamba.py:462)."""
     lib = _lib.load()
@@ -602,9 +651,10 @@ class FeedForwardFn(torch.autograd.Function):
         shape, xdt, w1dt, b1dt, w2dt, b2dt, has_res = ctx.meta
         with torch.autocast("cuda", enabled=False):
             cd = x2.dtype
-            g = dy.reshape(-1, W2T.shape[1]).to(cd)
+            g = dy.reshape(-1, W2T.shape[1])
             if g.stride(-1) != 1 or g.stride(0) != g.shape[1]:
                 g = g.contiguous()
+            g = cast(g, cd)
             with _Fork() as f2:                       # second Linear's parameter gradients || its data gradient
                 db2 = colsum(g)
                 dW2 = wgrad(g, a)
@@ -925,9 +975,10 @@ class BiMambaInnerFn(torch.autograd.Function):
             xs, z = xz3[:, :, :D], xz3[:, :, D:]
             xd4 = xdbl.view(Bsz, L, ndir, XW).permute(0, 2, 1, 3)
 
-            g2 = dout.to(cd).reshape(M, dm)
+            g2 = dout.reshape(M, dm)
             if g2.stride(1) != 1 or g2.stride(0) != dm:
                 g2 = g2.contiguous()
+            g2 = cast(g2, cd)
             # out_proj
             y2 = rows2d(y).view(M, ndir * D)
             with _Fork() as f_out:                                            # out_proj weight gradient || dy, scan

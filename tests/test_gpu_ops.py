@@ -419,3 +419,21 @@ def test_fp32_products_on_the_tensor_cores():
         A = torch.randn(M, N1, generator=g).cuda()
         B = torch.randn(M, N2, generator=g).cuda()
         assert rel(bm.ops.gemm_tn(A, B), A.double().t() @ B.double()) < 5e-5, (M, N1, N2)   # up to 154 k fp32-accumulated terms
+
+
+def test_cast_and_mean_square_loss_kernels():
+    g = torch.Generator().manual_seed(2)
+    for n in (12864 * 144, 1001, 7):
+        x = torch.randn(n, generator=g).cuda()
+        xb = bm.ops.cast(x, torch.bfloat16)
+        assert xb.dtype == torch.bfloat16 and torch.equal(xb, x.to(torch.bfloat16))
+        assert torch.equal(bm.ops.cast(xb, torch.float32), xb.float())
+    for dtype, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-6)):
+        x = torch.randn(64, 201, 144, generator=g).to(dtype).cuda().requires_grad_(True)
+        loss = bm.ops.mean_square_loss(x)
+        ref_in = x.detach().double().requires_grad_(True)
+        ref = ref_in.square().mean()
+        assert loss.dtype == torch.float32 and loss.ndim == 0 and rel(loss, ref) < tol
+        (3.0 * loss).backward()
+        (3.0 * ref).backward()
+        assert rel(x.grad, ref_in.grad) < (1e-6 if dtype == torch.float32 else 1e-2)
