@@ -9,7 +9,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbimamba_sm100.so")
+# BIMAMBA_LIB: an experiment build of the SAME library (build.py --variant, e.g. another -D flag) for A/B timing runs
+LIB_PATH = os.environ.get("BIMAMBA_LIB") or os.path.join(HERE, "libbimamba_sm100.so")
 
 F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1

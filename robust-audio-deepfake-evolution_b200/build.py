@@ -36,15 +36,30 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, defines=(), variant: str = "") -> str:
+    """Build the library.  `variant` + `defines` build an experiment copy `_variants/libbimamba_sm100_<variant>.so`
+    with extra -D flags (A/B runs load it through the BIMAMBA_LIB environment variable, see _lib.py)."""
+    if variant:
+        return _build_variant(variant, list(defines), verbose)
     if not force and not _stale():
         return LIB
+    return _compile(CSRC, LIB, [], verbose)
+
+
+def _build_variant(variant: str, defines, verbose: bool) -> str:
+    vdir = os.path.join(HERE, "_variants")
+    odir = os.path.join(vdir, "obj_" + variant)
+    os.makedirs(odir, exist_ok=True)
+    return _compile(odir, os.path.join(vdir, f"libbimamba_sm100_{variant}.so"), ["-D" + d for d in defines], verbose)
+
+
+def _compile(objdir: str, lib: str, extra, verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
     for s in SOURCES:
-        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", obj]
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((cmd, subprocess.Popen(cmd)))
@@ -52,12 +67,15 @@ def build(force: bool = False, verbose: bool = True) -> str:
     for cmd, p in procs:
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    # python build.py [--force] [--variant NAME -DX=1 ...]
+    argv = sys.argv[1:]
+    var = argv[argv.index("--variant") + 1] if "--variant" in argv else ""
+    print(build(force="--force" in argv, defines=[a[2:] for a in argv if a.startswith("-D")], variant=var))
