@@ -667,6 +667,27 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
     if (kv) persist = can_stage && kv == 2;
     if (persist) block_n = bnp;
   }
+  // Measured choices for the Phase-6 projection shapes at the benchmark's row counts (tools/sweep_gemm.py on a B200, eight
+  // back-to-back launches on rotating operands; profiles/r2_gemm_table.md): what decides is whether the tiles fit ONE wave
+  // at the TMEM / shared-memory occupancy of the configuration, and - for the long contractions - the persistent kernel's
+  // 4-stage ring and 8 epilogue warps even at one tile per CTA.
+  int tuned_stages = 0;
+  if (!kv && M >= 8192 && M <= 32768) {
+    struct Tuned { int N, K, persist, bn, stages; };
+    static const Tuned kTuned[] = {
+        {576, 144, 0, 128, 1},   // in_proj, FFN up, FFN-down data gradient: 14.2 -> 11.8 us (one stage = 4 CTAs / SM = one wave)
+        {144, 576, 1, 144, 0},   // out_proj, FFN down, in_proj / FFN-up data gradients: 11.9 -> 10.5 us
+        {288, 48, 0, 64, 1},     // x_proj data gradient: 11.8 -> 10.9 us
+        {48, 288, 0, 32, 2},     // x_proj: 9.7 -> 9.3 us
+    };
+    for (const Tuned& t : kTuned) {
+      if (t.N == N && t.K == K && (!t.persist || can_stage)) {
+        persist = t.persist != 0;
+        block_n = t.bn;
+        tuned_stages = t.stages;
+      }
+    }
+  }
   if (g_tune[BIMAMBA_TUNE_GEMM_BN]) block_n = g_tune[BIMAMBA_TUNE_GEMM_BN];            // tuning experiments only
   if (g_tune[BIMAMBA_TUNE_GEMM_STAGES]) max_stages = g_tune[BIMAMBA_TUNE_GEMM_STAGES];  // tuning experiments only
   CUtensorMap map_a, map_b;
@@ -675,7 +696,7 @@ extern "C" int bimamba_gemm_nt(const void* A, int64_t lda, const void* B, int64_
   rc = make_map(&map_b, B, in_dtype, N, K, ldb, block_n);
   if (rc) return rc;
   const uint32_t stage_bytes = kGM * kGK * 2 + (((uint32_t)block_n * kGK * 2 + 1023u) & ~1023u);
-  int stages = gemm_stages(block_n, K);
+  int stages = tuned_stages ? tuned_stages : gemm_stages(block_n, K);
   if (stages > max_stages) stages = max_stages;
   size_t smem = (size_t)stages * stage_bytes + 1024;
   // staged epilogue: 16-byte aligned output rows and a tile that fits next to (in place of) the stages
