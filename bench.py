@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scan sweep points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tune", default="", help="knob=value,... forwarded to bimamba_set_tuning (A/B measurements)")
-    ap.add_argument("--comm", default="overlap", choices=["overlap", "graph", "eager"],
+    ap.add_argument("--comm", default="overlap", choices=["overlap", "deferred", "graph", "eager"],
                     help="N > 1: gradient all-reduce per encoder layer inside the step graph, overlapping the remaining "
                          "backward (default); one all-reduce inside the graph; or launched after the graph (round 1)")
     return ap.parse_args()
@@ -341,17 +341,22 @@ def run_ours(args, rank, world, local_rank):
         for layer in model.backbone_layers:
             layer.mamba.A_log.add_(0.1 * torch.randn_like(layer.mamba.A_log))
     params = list(model.backbone_layers.parameters())
-    if world > 1:
+    # BENCH_FORCE_BUCKET=1 (diagnostic): the multi-GPU gradient-bucket path on ONE GPU - hooks, per-layer packs, the same
+    # graph structure, collectives degenerate to nothing - to separate the bucket's cost from the collectives'
+    bucketed = world > 1 or os.environ.get("BENCH_FORCE_BUCKET") == "1"
+    if bucketed:
         # one flat buffer; backward assigns the gradients, multi-tensor copies pack them, NCCL averages them
         bucket = bm.FlatGradBucket(params, accumulate=False)
         zero_grad = bucket.zero
         all_reduce = bucket.all_reduce_mean
         pack = bucket.pack
-        if args.comm == "overlap":      # one collective per encoder layer, issued when that layer's backward is done
-            bucket.enable_overlap([list(layer.parameters()) for layer in model.backbone_layers])
-        warm = torch.zeros(1, device="cuda")
-        dist.all_reduce(warm)           # communicator set-up outside any capture
-        torch.cuda.synchronize()
+        if args.comm in ("overlap", "deferred"):   # one collective per encoder layer, issued when that layer's backward is done
+            bucket.enable_overlap([list(layer.parameters()) for layer in model.backbone_layers],
+                                  defer_to_scan=args.comm == "deferred")
+        if world > 1:
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)           # communicator set-up outside any capture
+            torch.cuda.synchronize()
     else:                                       # single GPU: no collective, so no bucket; autograd assigns .grad
 
         def zero_grad():
@@ -377,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
         return bm.ops.mean_square_loss(out)          # mean(out^2) in fp32 (one launch forward, one backward)
 
     use_graph = not args.no_graph
-    if use_graph and world == 1:
+    if use_graph and not bucketed:
         runner = bm.GraphedTrainStep(fwd_loss, x_dev, zero_grad, opt, warmup=3)
 
         def step(x=None):
@@ -385,7 +390,7 @@ def run_ours(args, rank, world, local_rank):
     elif use_graph and args.comm != "eager":
         # multi-GPU: forward, backward, the per-layer gradient collectives (parallel branches that overlap the remaining
         # backward) and AdamW are ONE graph
-        if args.comm == "overlap":
+        if args.comm in ("overlap", "deferred"):
             post = bucket.finish_overlap
         else:
             def post():
@@ -409,7 +414,7 @@ def run_ours(args, rank, world, local_rank):
             zero_grad()
             loss = fwd_loss(x_dev if x is None else x.cuda(non_blocking=True))
             loss.backward()
-            if world > 1 and args.comm == "overlap":
+            if bucketed and args.comm in ("overlap", "deferred"):
                 bucket.finish_overlap()
             else:
                 if pack is not None:
@@ -422,7 +427,7 @@ def run_ours(args, rank, world, local_rank):
     bm._lib.launch_count = 0
     zero_grad()
     fwd_loss(x_dev).backward()
-    if world > 1 and args.comm == "overlap":
+    if bucketed and args.comm in ("overlap", "deferred"):
         bucket.finish_overlap()
     torch.cuda.synchronize()
     launches_per_step = bm._lib.launch_count + (0 if args.torch_adamw else 2)   # + AdamW: step tick + update
@@ -486,7 +491,7 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = load_peaks()
         timer = EventTimer()
         bm._lib.kernel_timer = timer
-        if world > 1 and args.comm == "overlap":
+        if bucketed and args.comm in ("overlap", "deferred"):
             bucket.disable_overlap()        # rank 0 alone runs this instrumented pass: no collectives
         for _ in range(3):
             flush.zero_()
@@ -537,7 +542,10 @@ def run_ours(args, rank, world, local_rank):
                            launch="CUDA-graph replay" if use_graph else "eager", state="fp32", weights="fp32 master, bf16 autocast",
                            gemm="tcgen05 (this repo)",
                            comm=(None if world == 1 else {"overlap": "NCCL all-reduce (AVG) per encoder layer inside the step "
-                                 "graph, overlapping the remaining backward", "graph": "one NCCL all-reduce inside the step graph",
+                                 "graph, overlapping the remaining backward",
+                                 "deferred": "NCCL all-reduce (AVG) per encoder layer inside the step graph, each issued after the "
+                                 "next layer's backward scan (no collective CTA resident when a scan launches)",
+                                 "graph": "one NCCL all-reduce inside the step graph",
                                  "eager": "one NCCL all-reduce after the graph"}[args.comm]),
                            optimizer="torch.optim.AdamW(fused)" if args.torch_adamw else "AdamW, one-launch kernel (this repo)"),
             "clocks": clocks,
