@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scan sweep points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tune", default="", help="knob=value,... forwarded to bimamba_set_tuning (A/B measurements)")
-    ap.add_argument("--comm", default="overlap", choices=["overlap", "deferred", "graph", "eager"],
+    ap.add_argument("--comm", default="overlap", choices=["overlap", "graph", "eager"],
                     help="N > 1: gradient all-reduce per encoder layer inside the step graph, overlapping the remaining "
                          "backward (default); one all-reduce inside the graph; or launched after the graph (round 1)")
     return ap.parse_args()
@@ -350,9 +350,8 @@ def run_ours(args, rank, world, local_rank):
         zero_grad = bucket.zero
         all_reduce = bucket.all_reduce_mean
         pack = bucket.pack
-        if args.comm in ("overlap", "deferred"):   # one collective per encoder layer, issued when that layer's backward is done
-            bucket.enable_overlap([list(layer.parameters()) for layer in model.backbone_layers],
-                                  defer_to_scan=args.comm == "deferred")
+        if args.comm == "overlap":      # one collective per encoder layer, issued when that layer's backward is done
+            bucket.enable_overlap([list(layer.parameters()) for layer in model.backbone_layers])
         if world > 1:
             warm = torch.zeros(1, device="cuda")
             dist.all_reduce(warm)           # communicator set-up outside any capture
@@ -390,7 +389,7 @@ def run_ours(args, rank, world, local_rank):
     elif use_graph and args.comm != "eager":
         # multi-GPU: forward, backward, the per-layer gradient collectives (parallel branches that overlap the remaining
         # backward) and AdamW are ONE graph
-        if args.comm in ("overlap", "deferred"):
+        if args.comm == "overlap":
             post = bucket.finish_overlap
         else:
             def post():
@@ -414,7 +413,7 @@ def run_ours(args, rank, world, local_rank):
             zero_grad()
             loss = fwd_loss(x_dev if x is None else x.cuda(non_blocking=True))
             loss.backward()
-            if bucketed and args.comm in ("overlap", "deferred"):
+            if bucketed and args.comm == "overlap":
                 bucket.finish_overlap()
             else:
                 if pack is not None:
@@ -427,7 +426,7 @@ def run_ours(args, rank, world, local_rank):
     bm._lib.launch_count = 0
     zero_grad()
     fwd_loss(x_dev).backward()
-    if bucketed and args.comm in ("overlap", "deferred"):
+    if bucketed and args.comm == "overlap":
         bucket.finish_overlap()
     torch.cuda.synchronize()
     launches_per_step = bm._lib.launch_count + (0 if args.torch_adamw else 2)   # + AdamW: step tick + update
@@ -491,7 +490,7 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = load_peaks()
         timer = EventTimer()
         bm._lib.kernel_timer = timer
-        if bucketed and args.comm in ("overlap", "deferred"):
+        if bucketed and args.comm == "overlap":
             bucket.disable_overlap()        # rank 0 alone runs this instrumented pass: no collectives
         for _ in range(3):
             flush.zero_()
@@ -543,8 +542,6 @@ def run_ours(args, rank, world, local_rank):
                            gemm="tcgen05 (this repo)",
                            comm=(None if world == 1 else {"overlap": "NCCL all-reduce (AVG) per encoder layer inside the step "
                                  "graph, overlapping the remaining backward",
-                                 "deferred": "NCCL all-reduce (AVG) per encoder layer inside the step graph, each issued after the "
-                                 "next layer's backward scan (no collective CTA resident when a scan launches)",
                                  "graph": "one NCCL all-reduce inside the step graph",
                                  "eager": "one NCCL all-reduce after the graph"}[args.comm]),
                            optimizer="torch.optim.AdamW(fused)" if args.torch_adamw else "AdamW, one-launch kernel (this repo)"),

@@ -68,17 +68,13 @@ class FlatGradBucket:
         self.attach()
 
     # ---- overlap: one collective per segment, launched as soon as backward has produced the segment's gradients -------
-    def enable_overlap(self, segments: List[List[torch.nn.Parameter]], group=None, defer_to_scan: bool = False):
+    def enable_overlap(self, segments: List[List[torch.nn.Parameter]], group=None):
         """accumulate=False only.  `segments` partitions the parameters (e.g. one list per encoder layer, in any order);
         a post-accumulate hook on every parameter counts arrivals and, when a segment is complete, packs it into its
         slice of the flat buffer and all-reduces that slice on a communication stream, so the collectives of layers
         N..2 run under the backward of layers N-1..1.  Call `finish_overlap()` after backward (GraphedTrainStep's
         post_backward): it joins the communication stream and re-points .grad at the views.  Under CUDA-graph capture
-        the hooks run once, at capture: the collectives become parallel branches of the captured graph.
-        defer_to_scan=True: a completed segment's collective is not issued at once but right after the NEXT backward scan
-        has been enqueued (ops.scan_bwd_listeners), i.e. it starts when that scan has finished.  The backward scan owns
-        every register of every SM in one wave; a collective whose CTAs are resident when it launches pushes part of that
-        wave behind itself.  Started after the scan, the collective runs beside the GEMM / conv kernels that follow."""
+        the hooks run once, at capture: the collectives become parallel branches of the captured graph."""
         if self.accumulate:
             raise ValueError("overlap needs accumulate=False (gradients are packed per segment)")
         index = {id(p): i for i, p in enumerate(self.params)}
@@ -97,11 +93,6 @@ class FlatGradBucket:
         if seen != set(range(len(self.params))):
             raise ValueError("segments must cover every parameter of the bucket")
         self._group = group
-        self._pending = []
-        self._defer = bool(defer_to_scan)
-        if self._defer:
-            from . import ops
-            ops.scan_bwd_listeners.append(self._flush_pending)
         self._comm = torch.cuda.Stream(device=self.flat.device) if self.flat.is_cuda else None   # CPU (gloo tests): inline
         seg_of = {i: s for s in self._segments for i in s["idx"]}
         for i, p in enumerate(self.params):
@@ -117,27 +108,15 @@ class FlatGradBucket:
                 src = [self.params[i].grad.to(self.dtype) for i in seg["idx"]]
                 torch._foreach_copy_([self.views[i] for i in seg["idx"]], src)
                 self._reduce(seg["flat"])
-            if self._defer:
-                self._pending.append(pack_and_reduce)
-            else:
-                self._issue(pack_and_reduce)
+            if self._comm is None:
+                pack_and_reduce()
+                return
+            self._comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm):
+                pack_and_reduce()
         return hook
 
-    def _issue(self, fn):
-        if self._comm is None:
-            fn()
-            return
-        self._comm.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._comm):
-            fn()
-
-    def _flush_pending(self):
-        pending, self._pending = self._pending, []
-        for fn in pending:
-            self._issue(fn)
-
     def finish_overlap(self):
-        self._flush_pending()
         if self._comm is not None:
             torch.cuda.current_stream().wait_stream(self._comm)
         for seg in self._segments:
@@ -148,11 +127,6 @@ class FlatGradBucket:
         for h in self._hooks:
             h.remove()
         self._hooks, self._segments = [], None
-        if getattr(self, "_defer", False):
-            from . import ops
-            if self._flush_pending in ops.scan_bwd_listeners:
-                ops.scan_bwd_listeners.remove(self._flush_pending)
-            self._defer = False
 
     def _reduce(self, flat):
         group = getattr(self, "_group", None)

@@ -36,10 +36,7 @@ def _worker(rank, world, port, q, accumulate=True, overlap=False):
     model = _make_model()
     bucket = dmod.FlatGradBucket(model.parameters(), accumulate=accumulate)
     if overlap:      # one collective per Linear layer, issued from post-accumulate hooks during backward
-        bucket.enable_overlap([list(model[0].parameters()), list(model[2].parameters())], defer_to_scan=overlap == "deferred")
-        if overlap == "deferred":   # collectives wait for the next backward scan: none has been issued by the hooks themselves
-            from bimamba_b200 import ops
-            assert bucket._flush_pending in ops.scan_bwd_listeners
+        bucket.enable_overlap([list(model[0].parameters()), list(model[2].parameters())])
     g = torch.Generator().manual_seed(1)
     x = torch.randn(10, 12, generator=g)
     y = torch.randn(10, 3, generator=g)
@@ -49,10 +46,6 @@ def _worker(rank, world, port, q, accumulate=True, overlap=False):
     loss = ((model(x[lo:hi]) - y[lo:hi]) ** 2).sum() / (10 / world)
     loss.backward()
     if overlap:
-        if overlap == "deferred":
-            assert len(bucket._pending) == 2      # both segments complete, nothing reduced yet (the toy model has no scan)
-            ops.scan_bwd_listeners[-1]()          # what a block's backward does after enqueueing its scan
-            assert not bucket._pending
         bucket.finish_overlap()
         flat = bucket.flat.clone()
     else:
@@ -79,10 +72,10 @@ def test_shard_batch_covers_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-@pytest.mark.parametrize("accumulate,overlap", [(True, False), (False, False), (False, True), (False, "deferred")])
+@pytest.mark.parametrize("accumulate,overlap", [(True, False), (False, False), (False, True)])
 def test_flat_bucket_allreduce_matches_full_batch(accumulate, overlap):
     """world_size 2 over gloo: the bucket modes (gradients accumulated into the flat buffer / packed after backward /
-    packed and all-reduced per segment from backward hooks, at once or deferred to the next backward scan) reproduce the single-process full-batch gradient."""
+    packed and all-reduced per segment from backward hooks) reproduce the single-process full-batch gradient."""
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
