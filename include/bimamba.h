@@ -25,6 +25,8 @@
  *   bimamba_layernorm_fwd/bwd        <- nn.LayerNorm of the encoder layer (DualStreamSEMamba.py:472,482)
  *   bimamba_gemm_nt                  <- the nn.Linear calls of mamba_block.py:48,73,62
  *                                       (in_proj, x_proj, out_proj) on tcgen05 tensor cores
+ *   bimamba_block_fwd/bwd            <- the whole block, both directions, one call each way
+ *                                       (mamba_block.py:41-63 + DualStreamSEMamba.py:473-481)
  *
  * Ownership: the library never allocates or frees device memory.  All tensors and
  * workspaces are caller-allocated; pointers are borrowed for the duration of the
@@ -42,7 +44,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 8
+#define BIMAMBA_ABI_VERSION 9
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -307,6 +309,66 @@ int bimamba_finalize_param_grads(const float* dA, const float* A, const float* d
                                  const float* dWo2, const float* dwb, float* dA_log, float* dWx, float* dWdt,
                                  float* dWo, float* dconv_w, float* dconv_b, int d_model, int d_inner, int d_state,
                                  int dt_rank, int ndir, int d_conv, bimamba_stream_t stream);
+
+/* ---- The whole Mamba block of one encoder layer in ONE call each way (`conv_scan_bi` together with
+ * gemm_{in,x,out}_proj and their data / weight gradients), for hosts without an autograd framework.
+ *   forward:  out = M(x) [+ flip(M(flip x))]   mamba_block.py:41-63 for M; DualStreamSEMamba.py:473-481 for the directions
+ *             in_proj -> conv + SiLU (both directions from one read) -> x_proj -> dt_proj + softplus + scan + D skip +
+ *             z gate (both directions, one launch) -> out_proj over [y_fwd | y_rev]:  5 kernels on `stream`
+ *   backward: the autograd of the above with every parameter gradient in the reference's layouts (mamba_block.py:22-39).
+ * x is the block's input AFTER norm1 (DualStreamSEMamba.py:472); activations are bf16 or fp16, contiguous
+ * (batch, seqlen, d_model); d_model and d_inner must be multiples of 8; d_state is 16.  Weights in io_dtype are the
+ * arrangements bimamba_pack_weights writes.  The forward keeps xz, xc, the x_proj rows, y (and, with
+ * save_for_backward, the scan checkpoints and the ungated y) in `workspace` (256-byte aligned,
+ * bimamba_block_fwd_workspace_bytes); the backward reads them from there and needs a scratch workspace of its own.
+ * Same kernels, same order of arithmetic as the Python autograd Function (ops.py: BiMambaInnerFn): results are
+ * bitwise identical to it. */
+typedef struct bimamba_block_desc {
+  const void* x;          /* (batch, seqlen, d_model)                                                   */
+  void* out;              /* (batch, seqlen, d_model)                                                   */
+  const void* Wi;         /* (2*d_inner, d_model)        in_proj.weight                                 */
+  const void* Wxp;        /* (48, d_inner)               x_proj.weight repacked [B | C | dt_r | 0]     */
+  const void* Wo2;        /* (d_model, ndir*d_inner)     [out_proj.weight] x ndir                       */
+  const float* Wdt;       /* (d_inner, dt_rank) fp32     dt_proj.weight                                 */
+  const float* A;         /* (d_inner, 16) fp32          -exp(A_log)                                    */
+  const float* D;         /* (d_inner) fp32                                                             */
+  const float* dt_bias;   /* (d_inner) fp32              dt_proj.bias                                   */
+  const float* conv_w;    /* (d_inner, d_conv) fp32      conv1d.weight                                  */
+  const float* conv_b;    /* (d_inner) fp32              conv1d.bias                                    */
+  void* workspace;        /* saved activations, bimamba_block_fwd_workspace_bytes(...) bytes            */
+  size_t workspace_bytes;
+  int32_t batch, seqlen, d_model, d_inner, dt_rank, d_conv, ndir, io_dtype;
+  int32_t save_for_backward; /* != 0: the forward also writes the scan checkpoints and the ungated y    */
+  int32_t reserved0;
+} bimamba_block_desc;
+
+typedef struct bimamba_block_grads {
+  const void* dout;       /* (batch, seqlen, d_model) io_dtype: gradient of the block output            */
+  void* dx;               /* (batch, seqlen, d_model) io_dtype                                          */
+  const void* WiT;        /* (d_model, 2*d_inner)  transposed arrangements of bimamba_pack_weights      */
+  const void* WxpT;       /* (d_inner, 48)                                                              */
+  const void* WoT;        /* (d_inner, d_model)                                                         */
+  const void* WdT;        /* (16, d_inner)                                                              */
+  float* dW_in;           /* (2*d_inner, d_model)   fp32 parameter gradients, the reference's shapes    */
+  float* dconv_w;         /* (d_inner, 1, d_conv)                                                       */
+  float* dconv_b;         /* (d_inner)                                                                  */
+  float* dW_x;            /* (dt_rank + 32, d_inner)  rows [dt_r | B | C]                               */
+  float* dW_dt;           /* (d_inner, dt_rank)                                                         */
+  float* db_dt;           /* (d_inner)                                                                  */
+  float* dA_log;          /* (d_inner, 16)                                                              */
+  float* dD;              /* (d_inner)                                                                  */
+  float* dW_out;          /* (d_model, d_inner)                                                         */
+  void* workspace;        /* scratch, bimamba_block_bwd_workspace_bytes(...) bytes, 256-byte aligned    */
+  size_t workspace_bytes;
+} bimamba_block_grads;
+
+size_t bimamba_block_fwd_workspace_bytes(int batch, int seqlen, int d_model, int d_inner, int ndir, int io_dtype,
+                                         int save_for_backward);
+size_t bimamba_block_bwd_workspace_bytes(int batch, int seqlen, int d_model, int d_inner, int d_conv, int ndir,
+                                         int io_dtype);
+int bimamba_block_fwd(const bimamba_block_desc* d, bimamba_stream_t stream);
+/* `d` is the descriptor the forward ran with (same workspace, save_for_backward != 0). */
+int bimamba_block_bwd(const bimamba_block_desc* d, const bimamba_block_grads* g, bimamba_stream_t stream);
 
 #ifdef __cplusplus
 }

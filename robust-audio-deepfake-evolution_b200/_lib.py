@@ -16,7 +16,7 @@ F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
 FLAG_DTR_PADDED = 2
 FLAG_SILU = 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 CHUNK = 16
 
 EXPORTS = (
@@ -27,6 +27,7 @@ EXPORTS = (
     "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_gemm_tn_splits", "bimamba_gemm_tn", "bimamba_adamw_chunk", "bimamba_adamw_step", "bimamba_head_fwd", "bimamba_colsum_slices", "bimamba_colsum", "bimamba_pack_weights", "bimamba_cast_transpose",
     "bimamba_gelu_fwd", "bimamba_gelu_bwd", "bimamba_reduce_rows32", "bimamba_finalize_param_grads", "bimamba_head_pool_bwd", "bimamba_set_tuning", "bimamba_get_tuning",
     "bimamba_scan_fwd_workspace_bytes", "bimamba_scan_bwd_workspace_bytes", "bimamba_split3_bf16", "bimamba_cast", "bimamba_sumsq_slices", "bimamba_sumsq", "bimamba_scale_by",
+    "bimamba_block_fwd_workspace_bytes", "bimamba_block_bwd_workspace_bytes", "bimamba_block_fwd", "bimamba_block_bwd",
 )
 
 
@@ -43,6 +44,26 @@ class ScanDesc(C.Structure):
             "u_bs", "u_ds", "u_ts", "z_bs", "z_ds", "z_ts", "delta_bs", "delta_ds", "delta_ts",
             "bc_bs", "bc_ds", "bc_ts", "dtr_bs", "dtr_ds", "dtr_ts", "out_bs", "out_ds", "out_ts",
             "dout_bs", "dout_ds", "dout_ts")]
+    )
+
+
+class BlockDesc(C.Structure):
+    """Mirror of `struct bimamba_block_desc` (include/bimamba.h): the whole block, forward."""
+    _fields_ = (
+        [(n, C.c_void_p) for n in ("x", "out", "Wi", "Wxp", "Wo2", "Wdt", "A", "D", "dt_bias", "conv_w", "conv_b",
+                                   "workspace")]
+        + [("workspace_bytes", C.c_size_t)]
+        + [(n, C.c_int32) for n in ("batch", "seqlen", "d_model", "d_inner", "dt_rank", "d_conv", "ndir", "io_dtype",
+                                    "save_for_backward", "reserved0")]
+    )
+
+
+class BlockGrads(C.Structure):
+    """Mirror of `struct bimamba_block_grads` (include/bimamba.h): the whole block, backward."""
+    _fields_ = (
+        [(n, C.c_void_p) for n in ("dout", "dx", "WiT", "WxpT", "WoT", "WdT", "dW_in", "dconv_w", "dconv_b", "dW_x",
+                                   "dW_dt", "db_dt", "dA_log", "dD", "dW_out", "workspace")]
+        + [("workspace_bytes", C.c_size_t)]
     )
 
 
@@ -151,6 +172,14 @@ def load() -> C.CDLL:
         lib.bimamba_sumsq.argtypes = [vp, vp, i64, C.c_float, i32, vp]
         lib.bimamba_scale_by.restype = i32
         lib.bimamba_scale_by.argtypes = [vp, vp, vp, i64, C.c_float, i32, vp]
+        lib.bimamba_block_fwd_workspace_bytes.restype = C.c_size_t
+        lib.bimamba_block_fwd_workspace_bytes.argtypes = [i32] * 7
+        lib.bimamba_block_bwd_workspace_bytes.restype = C.c_size_t
+        lib.bimamba_block_bwd_workspace_bytes.argtypes = [i32] * 7
+        lib.bimamba_block_fwd.restype = i32
+        lib.bimamba_block_fwd.argtypes = [C.POINTER(BlockDesc), vp]
+        lib.bimamba_block_bwd.restype = i32
+        lib.bimamba_block_bwd.argtypes = [C.POINTER(BlockDesc), C.POINTER(BlockGrads), vp]
         got = lib.bimamba_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError(f"libbimamba ABI {got} != expected {ABI_VERSION}; rebuild the library")

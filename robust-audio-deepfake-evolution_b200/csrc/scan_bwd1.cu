@@ -36,8 +36,6 @@
 namespace bimamba {
 
 constexpr int kLT = BIMAMBA_CKPT;   // steps per chunk == checkpoint interval (8)
-constexpr int kLMaxThreads = 128;
-constexpr int kRedRow = 36;         // floats per channel row of the dB|dC exchange: 32 + 4 pad (conflict-free 16-byte access)
 static_assert(kLT == 8, "history registers are sized for 8-step chunks");
 
 // kMode: 0 = delta given; 1 = fused dt projection with dt_rank <= 12; 2 = dt_rank <= 16.

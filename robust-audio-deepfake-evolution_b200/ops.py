@@ -914,9 +914,9 @@ class BiMambaInnerFn(torch.autograd.Function):
     Uses: in_proj(flip x) = flip(in_proj x) so xz is computed once; the reverse
     direction reads the same x, z back to front; out_proj is ONE GEMM over [y_fwd | y_rev] against
     [W_out | W_out].  The dt projection (K = 9) is fused into the scan kernels.
-    In bf16 / fp16 the forward and data-gradient GEMMs run on this repository's tcgen05 kernel (gemm_nt);
-    weight-gradient GEMMs (contraction over B*L) and the fp32 parity mode use the library GEMM.  Conv, scan,
-    dt_proj and all reductions are this repository's CUDA kernels.
+    Every product runs on this repository's tcgen05 kernels: forward and data-gradient GEMMs on gemm_nt, weight
+    gradients (contraction over B*L) on gemm_tn, fp32 operands through the three-term bf16 split (_split3).  Conv,
+    scan, dt_proj and all reductions are this repository's CUDA kernels too.
     """
 
     @staticmethod
@@ -1039,3 +1039,68 @@ def bimamba_inner_fn(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out,
         compute_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
     return BiMambaInnerFn.apply(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bool(bidirectional),
                                 compute_dtype, _wants_grad(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out))
+
+
+# ----------------------------------------------------------------------------------------
+# the same block through the ONE-CALL native entry points (bimamba_block_fwd / bimamba_block_bwd): what a host without an
+# autograd framework binds.  The autograd Function above stays the Python product path (it overlaps the weight-gradient
+# products on a side stream); these wrappers exist so that the entry points are exercised against it bit for bit.
+# ----------------------------------------------------------------------------------------
+class NativeBlock:
+    """State of one forward call of the native block: descriptor, saved-activation workspace, packed weights."""
+
+    def __init__(self, x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bidirectional=True,
+                 save_for_backward=True):
+        _require_cuda(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out)
+        if x.dtype not in (torch.bfloat16, torch.float16):
+            raise TypeError("the native block entry points take bf16 / fp16 activations")
+        lib = _lib.load()
+        Bsz, L, dm = x.shape
+        D = W_in.shape[0] // 2
+        R = W_dt.shape[1]
+        ndir = 2 if bidirectional else 1
+        self.x = x.contiguous()
+        self.shape = (Bsz, L, dm, D, R, ndir)
+        self.packed = pack_weights(W_in.detach(), W_x.detach(), W_dt.detach(), A_log.detach(), W_out.detach(), ndir, x.dtype)
+        Wi, WiT, Wxp, WxpT, Wo2, WoT, WdT, A32 = self.packed
+        self.f32 = (_f32c(W_dt.detach()), _f32c(conv_w.detach()).reshape(D, -1), _f32c(conv_b.detach()),
+                    _f32c(Dp.detach()), _f32c(b_dt.detach()))
+        Wd32, cw32, cb32, D32, bdt32 = self.f32
+        K = cw32.shape[1]
+        self.K = K
+        nbytes = lib.bimamba_block_fwd_workspace_bytes(Bsz, L, dm, D, ndir, _dt(x), int(save_for_backward))
+        self.ws = torch.empty((max(nbytes, 1),), device=x.device, dtype=torch.uint8)
+        self.out = torch.empty_like(self.x)
+        d = _lib.BlockDesc()
+        d.x, d.out = _ptr(self.x), _ptr(self.out)
+        d.Wi, d.Wxp, d.Wo2 = _ptr(Wi), _ptr(Wxp), _ptr(Wo2)
+        d.Wdt, d.A, d.D, d.dt_bias, d.conv_w, d.conv_b = (_ptr(Wd32), _ptr(A32), _ptr(D32), _ptr(bdt32), _ptr(cw32),
+                                                          _ptr(cb32))
+        d.workspace, d.workspace_bytes = _ptr(self.ws), nbytes
+        d.batch, d.seqlen, d.d_model, d.d_inner, d.dt_rank, d.d_conv, d.ndir = Bsz, L, dm, D, R, K, ndir
+        d.io_dtype, d.save_for_backward = _dt(x), int(save_for_backward)
+        self.desc = d
+        _lib.check(lib.bimamba_block_fwd(C.byref(d), _stream()), "bimamba_block_fwd")
+
+    def backward(self, dout):
+        """-> (dx, dW_in, dconv_w, dconv_b, dW_x, dW_dt, db_dt, dA_log, dD, dW_out), fp32 parameter gradients in the
+        reference's shapes."""
+        lib = _lib.load()
+        Bsz, L, dm, D, R, ndir = self.shape
+        K, N = self.K, D_STATE
+        Wi, WiT, Wxp, WxpT, Wo2, WoT, WdT, A32 = self.packed
+        dev, f32 = self.x.device, torch.float32
+        dout = dout.to(self.x.dtype).contiguous()
+        dx = torch.empty_like(self.x)
+        grads = [torch.empty(s, device=dev, dtype=f32) for s in
+                 ((2 * D, dm), (D, 1, K), (D,), (R + 2 * N, D), (D, R), (D,), (D, N), (D,), (dm, D))]
+        nbytes = lib.bimamba_block_bwd_workspace_bytes(Bsz, L, dm, D, K, ndir, _dt(self.x))
+        ws = torch.empty((max(nbytes, 1),), device=dev, dtype=torch.uint8)
+        g = _lib.BlockGrads()
+        g.dout, g.dx = _ptr(dout), _ptr(dx)
+        g.WiT, g.WxpT, g.WoT, g.WdT = _ptr(WiT), _ptr(WxpT), _ptr(WoT), _ptr(WdT)
+        (g.dW_in, g.dconv_w, g.dconv_b, g.dW_x, g.dW_dt, g.db_dt, g.dA_log, g.dD, g.dW_out) = [_ptr(t) for t in grads]
+        g.workspace, g.workspace_bytes = _ptr(ws), nbytes
+        _lib.check(lib.bimamba_block_bwd(C.byref(self.desc), C.byref(g), _stream()), "bimamba_block_bwd")
+        self._keep = (dout, ws)
+        return (dx, *grads)

@@ -32,19 +32,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.bimamba_abi_version() == bm._lib.ABI_VERSION
 
 
-def test_scan_desc_layout_matches_header(tmp_path):
-    """sizeof / offsetof of the ctypes mirror against the C compiler's view of the header."""
+@pytest.mark.parametrize("cname,mirror", [("bimamba_scan_desc", "ScanDesc"), ("bimamba_block_desc", "BlockDesc"),
+                                          ("bimamba_block_grads", "BlockGrads")])
+def test_struct_layouts_match_header(tmp_path, cname, mirror):
+    """sizeof / offsetof of the ctypes mirrors against the C compiler's view of the header."""
+    cls = getattr(bm._lib, mirror)
     prog = tmp_path / "layout.c"
-    fields = [f[0] for f in bm._lib.ScanDesc._fields_]
-    body = "\n".join(f'  printf("{f} %zu\\n", offsetof(bimamba_scan_desc, {f}));' for f in fields)
+    fields = [f[0] for f in cls._fields_]
+    body = "\n".join(f'  printf("{f} %zu\\n", offsetof({cname}, {f}));' for f in fields)
     prog.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{HEADER}"\nint main(void) {{\n'
-                    f'  printf("sizeof %zu\\n", sizeof(bimamba_scan_desc));\n{body}\n  return 0;\n}}\n')
+                    f'  printf("sizeof %zu\\n", sizeof({cname}));\n{body}\n  return 0;\n}}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c99", str(prog), "-o", str(exe)])
     out = dict(ln.split() for ln in subprocess.check_output([str(exe)], text=True).splitlines())
-    assert int(out["sizeof"]) == C.sizeof(bm._lib.ScanDesc)
+    assert int(out["sizeof"]) == C.sizeof(cls)
     for f in fields:
-        assert int(out[f]) == getattr(bm._lib.ScanDesc, f).offset, f
+        assert int(out[f]) == getattr(cls, f).offset, f
 
 
 def test_argument_errors_are_codes_not_exceptions():
@@ -140,3 +143,41 @@ def test_workspace_queries_and_tuning_knobs():
     assert lib.bimamba_reduce_rows32(None, None, 2, 9, 402, 48, 1, None) == -1
     assert lib.bimamba_head_pool_bwd(None, None, None, None, None, None, None, None, 2, 5, 144, 1e-5, 0, None) == -1
     assert lib.bimamba_finalize_param_grads(*([None] * 12), 144, 288, 16, 9, 2, 4, None) == -1
+
+
+def test_native_block_entry_points_host_side():
+    """bimamba_block_fwd / bimamba_block_bwd (the whole block in one call each way): workspace sizes follow the documented
+    carve (256-byte aligned pieces), argument errors are codes, empty problems are a no-op success."""
+    lib = bm._lib.load()
+    B, L, dm, D, ndir, K, N = 64, 201, 144, 288, 2, 4, 16
+    up = lambda v: (v + 255) // 256 * 256
+    M, es, nck = B * L, 2, -(-L // 8)
+    infer = up(M * 2 * D * es) + up(M * ndir * D * es) + up(M * ndir * 48 * es) + up(M * ndir * D * es)
+    train = infer + up(B * ndir * nck * D * N * 4) + up(M * ndir * D * es)
+    assert lib.bimamba_block_fwd_workspace_bytes(B, L, dm, D, ndir, bm._lib.BF16, 0) == infer
+    assert lib.bimamba_block_fwd_workspace_bytes(B, L, dm, D, ndir, bm._lib.BF16, 1) == train
+    assert lib.bimamba_block_fwd_workspace_bytes(2, 8, dm, D, ndir, bm._lib.BF16, 1) == (      # one chunk: no checkpoints
+        up(16 * 2 * D * es) + 2 * up(16 * ndir * D * es) + up(16 * ndir * 48 * es) + up(16 * ndir * D * es))
+    assert lib.bimamba_block_fwd_workspace_bytes(0, L, dm, D, ndir, bm._lib.BF16, 1) == 0
+    bwd = lib.bimamba_block_bwd_workspace_bytes(B, L, dm, D, K, ndir, bm._lib.BF16)
+    ng = bm._lib.scan_plan(L, D, B * ndir, True)[1]
+    # at least: the activation-sized gradients + the scan's partial rows
+    floor = M * D * es + 4 * M * ndir * D * es + M * ndir * 48 * es + M * 2 * D * es + B * ng * L * ndir * 2 * N * 4
+    assert floor < bwd < 2 * floor
+    assert bwd % 256 == 0
+    # errors are codes
+    assert lib.bimamba_block_fwd(None, None) == -1
+    d = bm._lib.BlockDesc()
+    d.batch, d.seqlen, d.d_model, d.d_inner, d.dt_rank, d.d_conv, d.ndir = 2, 5, 144, 288, 9, 4, 2
+    d.io_dtype = bm._lib.F32
+    assert lib.bimamba_block_fwd(C.byref(d), None) == -6                   # fp32 goes through the op-level entries
+    assert b"bf16 or fp16" in lib.bimamba_last_error()
+    d.io_dtype = bm._lib.BF16
+    d.d_model = 20
+    assert lib.bimamba_block_fwd(C.byref(d), None) == -7                   # d_model must be a multiple of 8
+    d.d_model = 144
+    assert lib.bimamba_block_fwd(C.byref(d), None) == -7                   # null operands
+    d.ndir = 3
+    assert lib.bimamba_block_fwd(C.byref(d), None) == -3
+    d.ndir = 2
+    assert lib.bimamba_block_bwd(C.byref(d), None, None) < 0

@@ -1,0 +1,92 @@
+"""The one-call native entry points bimamba_block_fwd / bimamba_block_bwd (include/bimamba.h; SURVEY 8b `conv_scan_bi` +
+projections) on the GPU: against the fp64 oracle (outputs and every gradient, bf16 tolerance 2e-2) and, bit for bit,
+against the Python autograd Function that sequences the same kernels (ops.py: BiMambaInnerFn)."""
+import ctypes as C
+
+import pytest
+import torch
+
+import bimamba_b200 as bm
+from bimamba_b200 import ops
+from oracle import bimamba_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ("in_proj.weight", "conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight", "dt_proj.bias", "A_log", "D",
+         "out_proj.weight")
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _params(d_model, seed):
+    p64 = orc.init_mamba_params(d_model, 16, seed=seed, dtype=torch.float64)
+    return p64, [p64[n].float().cuda() for n in NAMES]
+
+
+@pytest.mark.parametrize("d_model,Bsz,L,bidir,dtype", [
+    (144, 3, 201, True, torch.bfloat16),      # the Phase-6 shape
+    (144, 2, 5, True, torch.bfloat16),        # a single chunk: no checkpoints
+    (64, 2, 260, True, torch.bfloat16),       # another width (d_inner 128, dt_rank 4)
+    (144, 2, 77, False, torch.bfloat16),      # one direction: Mamba.forward
+    (144, 2, 201, True, torch.float16),       # the reference's training dtype (src/main.py:1049)
+])
+def test_native_block_equals_autograd_function_bitwise(d_model, Bsz, L, bidir, dtype):
+    _, w = _params(d_model, seed=L)
+    g = torch.Generator().manual_seed(L)
+    x = torch.randn(Bsz, L, d_model, generator=g).cuda().to(dtype)
+    cot = torch.randn(Bsz, L, d_model, generator=g).cuda().to(dtype)
+    # Python product path
+    wp = [t.clone().requires_grad_(True) for t in w]
+    xp = x.clone().requires_grad_(True)
+    out_p = ops.bimamba_inner_fn(xp, *wp, bidirectional=bidir, compute_dtype=dtype)
+    out_p.backward(cot)
+    # native one-call path
+    nb = ops.NativeBlock(x, *w, bidirectional=bidir, save_for_backward=True)
+    grads = nb.backward(cot)
+    torch.cuda.synchronize()
+    assert torch.equal(nb.out, out_p.detach())
+    assert torch.equal(grads[0], xp.grad)
+    for name, gn, p in zip(NAMES, grads[1:], wp):
+        assert gn.shape == p.grad.shape, name
+        assert torch.equal(gn, p.grad), name
+    # inference call (no checkpoints / ungated y written): same output from a smaller workspace
+    nb2 = ops.NativeBlock(x, *w, bidirectional=bidir, save_for_backward=False)
+    torch.cuda.synchronize()
+    assert nb2.ws.numel() < nb.ws.numel()
+    assert torch.equal(nb2.out, nb.out)
+
+
+def test_native_block_vs_oracle_bf16():
+    """Outputs and every gradient of the native calls against the fp64 oracle on bf16-rounded inputs (north_star: 2e-2)."""
+    p64, w = _params(144, seed=11)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(4, 201, 144, generator=g).bfloat16()
+    cot = torch.randn(4, 201, 144, generator=g).bfloat16()
+    pr = {k: v.float().double().requires_grad_(True) for k, v in p64.items()}
+    xr = x.double().requires_grad_(True)
+    ref = orc.bimamba_ref(pr, xr)
+    (ref * cot.double()).sum().backward()
+    nb = ops.NativeBlock(x.cuda(), *w)
+    grads = nb.backward(cot.cuda())
+    assert rel(nb.out, ref) < 2e-2
+    assert rel(grads[0], xr.grad) < 2e-2
+    for name, gn in zip(NAMES, grads[1:]):
+        assert rel(gn, pr[name].grad) < 2e-2, name
+
+
+def test_native_block_argument_errors_on_device():
+    """Workspace too small / missing save_for_backward come back as codes with a message; nothing is launched."""
+    _, w = _params(144, seed=3)
+    x = torch.randn(2, 40, 144, device="cuda").bfloat16()
+    nb = ops.NativeBlock(x, *w, save_for_backward=False)
+    lib = bm._lib.load()
+    with pytest.raises(RuntimeError, match="save_for_backward"):
+        nb.backward(torch.zeros_like(x))
+    d = nb.desc
+    d.workspace_bytes = 16
+    assert lib.bimamba_block_fwd(C.byref(d), None) == -10
+    assert b"workspace too small" in lib.bimamba_last_error()
