@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 9
+#define BIMAMBA_ABI_VERSION 10
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -127,7 +127,8 @@ const char* bimamba_last_error(void);
 #define BIMAMBA_TUNE_GEMM_BN 3      /* tile width override                                                         */
 #define BIMAMBA_TUNE_GEMM_STAGES 4  /* TMA ring depth override                                                     */
 #define BIMAMBA_TUNE_PDL 5          /* 1 = launch without programmatic dependent launch (A/B measurements)         */
-#define BIMAMBA_TUNE_COUNT 6
+#define BIMAMBA_TUNE_SCAN_SPLIT 6   /* forward scan time split: 1 = never, k >= 2 = k segments at any size (parity tests) */
+#define BIMAMBA_TUNE_COUNT 7
 int bimamba_set_tuning(int knob, int value);
 int bimamba_get_tuning(int knob);
 
@@ -144,6 +145,20 @@ int bimamba_scan_plan(int seqlen, int dim, int rows, int backward, int* group_ch
 
 int bimamba_selective_scan_fwd(const bimamba_scan_desc* d, bimamba_stream_t stream);
 int bimamba_selective_scan_bwd(const bimamba_scan_desc* d, bimamba_stream_t stream);
+
+/* Time-parallel forward scan for long sequences at small batches (the scan as an associative operator on pairs,
+ * (a2, b2) o (a1, b1) = (a2 a1, a2 b1 + b2); mamba_block.py:92-117 is the serial loop).  Scan time is cut into nseg
+ * segments of seg_len steps: a carry pass computes every segment's end state from zero and its decay exponent
+ * sum_t delta_t, the output pass starts each segment from the carries combined in order.  Same descriptor, outputs,
+ * ypre and checkpoints as bimamba_selective_scan_fwd (the backward is unchanged); results differ from the unsplit call
+ * by fp32 rounding only (exp(A sum delta) against the product of per-step decays).
+ * bimamba_scan_fwd_split_plan returns *nseg = 1 when splitting does not pay (enough channel lanes to fill the GPU, a
+ * short sequence, or fp32 I/O - measured slower): then call bimamba_selective_scan_fwd.  carry: caller-allocated fp32 workspace of
+ * bimamba_scan_fwd_split_workspace_bytes(batch, ndir, dim, nseg) bytes, 16-byte aligned. */
+int bimamba_scan_fwd_split_plan(int batch, int ndir, int seqlen, int dim, int io_dtype, int* nseg, int* seg_len);
+size_t bimamba_scan_fwd_split_workspace_bytes(int batch, int ndir, int dim, int nseg);
+int bimamba_selective_scan_fwd_split(const bimamba_scan_desc* d, int nseg, int seg_len, float* carry, size_t carry_bytes,
+                                     bimamba_stream_t stream);
 
 /* Depthwise causal conv, channel-last.  x: (batch, L, dim) with strides x_bs, x_ts;
  * out: (batch, ndir, L, dim) with strides out_bs, out_ds, out_ts.  dir 0: taps t-(K-1)..t;

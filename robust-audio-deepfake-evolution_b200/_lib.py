@@ -16,7 +16,7 @@ F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
 FLAG_DTR_PADDED = 2
 FLAG_SILU = 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 CHUNK = 16
 
 EXPORTS = (
@@ -27,6 +27,7 @@ EXPORTS = (
     "bimamba_gemm_nt_block_n", "bimamba_gemm_nt_block_n_k", "bimamba_gemm_nt", "bimamba_gemm_tn_splits", "bimamba_gemm_tn", "bimamba_adamw_chunk", "bimamba_adamw_step", "bimamba_head_fwd", "bimamba_colsum_slices", "bimamba_colsum", "bimamba_pack_weights", "bimamba_cast_transpose",
     "bimamba_gelu_fwd", "bimamba_gelu_bwd", "bimamba_reduce_rows32", "bimamba_finalize_param_grads", "bimamba_head_pool_bwd", "bimamba_set_tuning", "bimamba_get_tuning",
     "bimamba_scan_fwd_workspace_bytes", "bimamba_scan_bwd_workspace_bytes", "bimamba_split3_bf16", "bimamba_cast", "bimamba_sumsq_slices", "bimamba_sumsq", "bimamba_scale_by",
+    "bimamba_scan_fwd_split_plan", "bimamba_scan_fwd_split_workspace_bytes", "bimamba_selective_scan_fwd_split",
     "bimamba_block_fwd_workspace_bytes", "bimamba_block_bwd_workspace_bytes", "bimamba_block_fwd", "bimamba_block_bwd",
 )
 
@@ -180,6 +181,12 @@ def load() -> C.CDLL:
         lib.bimamba_block_fwd.argtypes = [C.POINTER(BlockDesc), vp]
         lib.bimamba_block_bwd.restype = i32
         lib.bimamba_block_bwd.argtypes = [C.POINTER(BlockDesc), C.POINTER(BlockGrads), vp]
+        lib.bimamba_scan_fwd_split_plan.restype = i32
+        lib.bimamba_scan_fwd_split_plan.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        lib.bimamba_scan_fwd_split_workspace_bytes.restype = C.c_size_t
+        lib.bimamba_scan_fwd_split_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        lib.bimamba_selective_scan_fwd_split.restype = i32
+        lib.bimamba_selective_scan_fwd_split.argtypes = [C.POINTER(ScanDesc), i32, i32, vp, C.c_size_t, vp]
         got = lib.bimamba_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError(f"libbimamba ABI {got} != expected {ABI_VERSION}; rebuild the library")
@@ -195,6 +202,13 @@ def check(rc: int, what: str) -> None:
     launch_count += 1
 
 
+def scan_split_plan(batch: int, ndir: int, seqlen: int, dim: int, io_dtype: int = BF16):
+    """-> (nseg, seg_len) of the time-parallel forward scan; nseg == 1: do not split."""
+    ns, sl = C.c_int(1), C.c_int(0)
+    load().bimamba_scan_fwd_split_plan(int(batch), int(ndir), int(seqlen), int(dim), int(io_dtype), C.byref(ns), C.byref(sl))
+    return ns.value, sl.value
+
+
 def scan_plan(seqlen: int, dim: int, rows: int, backward: bool = False):
     """-> (group_channels, ngroups, nchunks)"""
     gc, ng = C.c_int(0), C.c_int(0)
@@ -203,7 +217,7 @@ def scan_plan(seqlen: int, dim: int, rows: int, backward: bool = False):
     return g, (dim + g - 1) // g, n
 
 
-TUNE_SCAN_FWD, TUNE_CONV_BWD, TUNE_GEMM_KERNEL, TUNE_GEMM_BN, TUNE_GEMM_STAGES, TUNE_PDL = range(6)
+TUNE_SCAN_FWD, TUNE_CONV_BWD, TUNE_GEMM_KERNEL, TUNE_GEMM_BN, TUNE_GEMM_STAGES, TUNE_PDL, TUNE_SCAN_SPLIT = range(7)
 
 
 class tuning:

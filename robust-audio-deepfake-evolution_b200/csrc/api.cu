@@ -12,7 +12,7 @@ void set_err(const char* msg) {
 
 // Tuning knobs (tests and tuning experiments force kernel variants through bimamba_set_tuning; launches read these
 // process-wide integers - no getenv on any launch path).  0 = automatic choice.
-int g_tune[BIMAMBA_TUNE_COUNT] = {0, 0, 0, 0, 0, 0};
+int g_tune[BIMAMBA_TUNE_COUNT] = {0, 0, 0, 0, 0, 0, 0};
 
 int check_desc(const bimamba_scan_desc* d, bool bwd) {
   if (!d) { set_err("null descriptor"); return -1; }

@@ -237,6 +237,16 @@ def scan_fwd_raw(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus: bool, wa
     d = _fill_desc(u, z, delta, bc, dtr, Wdt, A, D, delta_bias, softplus, dtr_padded, G)
     d.out, d.ypre, d.ckpt = _ptr(out), _ptr(ypre), _ptr(ckpt)
     d.out_bs, d.out_ds, d.out_ts = _s3(out)
+    nseg, seg_len = _lib.scan_split_plan(Bsz, ndir, L, dim, _dt(u))
+    if nseg > 1:
+        # long sequence, few channel lanes: time-parallel scan (carry pass + output pass, two launches)
+        nbytes = lib.bimamba_scan_fwd_split_workspace_bytes(Bsz, ndir, dim, nseg)
+        carry = torch.empty((nbytes // 4,), device=u.device, dtype=torch.float32)
+        with _timed("scan_fwd"):
+            _lib.check(lib.bimamba_selective_scan_fwd_split(C.byref(d), nseg, seg_len, _ptr(carry), nbytes, _stream()),
+                       "bimamba_selective_scan_fwd_split")
+        _lib.launch_count += 1   # two kernels per call
+        return out, ckpt, ypre
     with _timed("scan_fwd"):
         _lib.check(lib.bimamba_selective_scan_fwd(C.byref(d), _stream()), "bimamba_selective_scan_fwd")
     return out, ckpt, ypre

@@ -181,3 +181,38 @@ def test_native_block_entry_points_host_side():
     assert lib.bimamba_block_fwd(C.byref(d), None) == -3
     d.ndir = 2
     assert lib.bimamba_block_bwd(C.byref(d), None, None) < 0
+
+
+def test_time_split_plan_and_errors_host_side():
+    """bimamba_scan_fwd_split_plan: only long walks on an under-filled GPU split; segments are whole 16-step chunks and the
+    last one is never empty; the knob forces a segment count for the parity tests; argument errors are codes."""
+    lib = bm._lib.load()
+    assert bm._lib.scan_split_plan(64, 1, 8192, 288) == (3, 2736)       # config 5, last point: 576 warps -> 3 segments
+    assert bm._lib.scan_split_plan(1, 1, 8192, 288) == (8, 1024)
+    assert bm._lib.scan_split_plan(64, 1, 8192, 288, bm._lib.F32) == (1, 8192)   # fp32 I/O: the serial walk was measured faster
+    assert bm._lib.scan_split_plan(64, 1, 8192, 288, bm._lib.F16) == (3, 2736)
+    assert bm._lib.scan_split_plan(64, 2, 201, 288) == (1, 201)         # the Phase-6 training shape never splits
+    assert bm._lib.scan_split_plan(128, 1, 4096, 288) == (1, 4096)      # 1152 warps fill the GPU
+    assert bm._lib.scan_split_plan(8, 1, 1024, 288) == (1, 1024)        # short walk
+    with bm._lib.tuning(bm._lib.TUNE_SCAN_SPLIT, 4):
+        assert bm._lib.scan_split_plan(2, 2, 201, 288) == (4, 64)
+        assert bm._lib.scan_split_plan(2, 2, 37, 40) == (3, 16)
+        assert bm._lib.scan_split_plan(1, 1, 1, 8) == (1, 1)
+    with bm._lib.tuning(bm._lib.TUNE_SCAN_SPLIT, 1):
+        assert bm._lib.scan_split_plan(64, 1, 8192, 288) == (1, 8192)
+    for L in (17, 201, 499, 8192, 10000):
+        for force in (2, 3, 5, 8):
+            with bm._lib.tuning(bm._lib.TUNE_SCAN_SPLIT, force):
+                ns, sl = bm._lib.scan_split_plan(2, 1, L, 64)
+            assert ns == 1 or (sl % 16 == 0 and (ns - 1) * sl < L <= ns * sl), (L, force, ns, sl)
+    assert lib.bimamba_scan_fwd_split_workspace_bytes(64, 1, 288, 3) == 64 * 2 * 288 * 17 * 4
+    assert lib.bimamba_scan_fwd_split_workspace_bytes(64, 1, 288, 1) == 0
+    # validation happens before any launch: a descriptor with fake (non-null) pointers and a bad segmentation
+    d = bm._lib.ScanDesc()
+    d.batch, d.ndir, d.dim, d.seqlen, d.dstate, d.group_channels = 2, 1, 32, 100, 16, 32
+    d.u = d.A = d.bc = d.delta = d.out = 4096
+    assert lib.bimamba_selective_scan_fwd_split(C.byref(d), 3, 40, None, 0, None) == -5       # not whole chunks
+    assert lib.bimamba_selective_scan_fwd_split(C.byref(d), 3, 64, None, 0, None) == -5       # last segment empty
+    assert lib.bimamba_selective_scan_fwd_split(C.byref(d), 2, 64, None, 0, None) == -10      # no carry workspace
+    assert b"carry workspace" in lib.bimamba_last_error()
+    assert lib.bimamba_selective_scan_fwd_split(None, 2, 64, None, 0, None) == -1

@@ -90,6 +90,16 @@ def test_bidirectional_block_conv_tile_variant(Bsz, L):
         test_bidirectional_block_fp32_vs_oracle(Bsz, L)
 
 
+@pytest.mark.parametrize("Bsz,L,nseg", [(3, 201, 3), (2, 499, 4), (2, 260, 2)])
+def test_bidirectional_block_time_split_forward(Bsz, L, nseg):
+    """The time-parallel forward scan forced inside the fused block (dt projection in the kernel, both directions, gate,
+    checkpoints + ungated y for the backward): outputs and every gradient against the oracle, fp32, 1e-4."""
+    with bm._lib.tuning(bm._lib.TUNE_SCAN_SPLIT, nseg):
+        test_bidirectional_block_fp32_vs_oracle(Bsz, L)
+        if nseg == 3:
+            test_block_bf16_autocast_vs_oracle()
+
+
 def test_block_bf16_autocast_vs_oracle():
     """Config-2 numerics: bf16 activations / fp32 state under autocast; oracle in fp64 on the same
     fp32 master weights.  Tolerance 2e-2 relative."""

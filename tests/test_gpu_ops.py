@@ -437,3 +437,43 @@ def test_cast_and_mean_square_loss_kernels():
         (3.0 * loss).backward()
         (3.0 * ref).backward()
         assert rel(x.grad, ref_in.grad) < (1e-6 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("nseg", [2, 3, 5])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scan_forward_time_split(nseg, dtype):
+    """The time-parallel forward (carry pass over the segments, then the output pass from the combined carries;
+    bimamba_selective_scan_fwd_split) forced at small sizes through bimamba_set_tuning: the output and - through the
+    checkpoints and the ungated y it writes - every gradient against the fp64 oracle, on ragged lengths and channel
+    counts and with every optional operand absent."""
+    with bm._lib.tuning(bm._lib.TUNE_SCAN_SPLIT, nseg):
+        for L, D in ((201, 288), (37, 40), (499, 17), (1024, 24)):
+            assert bm._lib.scan_split_plan(2, 1, L, D, bm._lib.F32)[0] >= 2
+            errs = _run_both(2, D, L, dtype, seed=L + D)
+            assert max(errs.values()) < TOL[dtype], (nseg, L, D, errs)
+        errs = _run_both(2, 40, 77, dtype, with_z=False, with_D=False, with_bias=False, softplus=False, seed=5)
+        assert max(errs.values()) < TOL[dtype], errs
+
+
+def test_scan_time_split_is_automatic_at_long_lengths_and_matches_the_serial_walk():
+    """L = 8192 at a small batch with 16-bit I/O (config 5's last point) takes the time-parallel path by itself; the
+    Phase-6 training shape and fp32 I/O never do.  Split against the serial walk of the same kernel family (knob = 1):
+    rounding only; both against the fp64 oracle."""
+    assert bm._lib.scan_split_plan(64, 1, 8192, 288, bm._lib.BF16) == (3, 2736)
+    assert bm._lib.scan_split_plan(64, 1, 8192, 288, bm._lib.F32)[0] == 1
+    assert bm._lib.scan_split_plan(64, 2, 201, 288, bm._lib.BF16)[0] == 1
+    assert bm._lib.scan_split_plan(2048, 1, 256, 288, bm._lib.BF16)[0] == 1
+    for dtype, tol_pair in ((torch.bfloat16, 1e-2), (torch.float32, 1e-4)):
+        u, delta, z, Bm, Cm, A, Dp, bias = _scan_inputs(3, 72, 8192, seed=21, dtype=dtype)
+        dev = [t.cuda() for t in (u, delta, A, Bm, Cm, Dp, z, bias)]
+        auto = bm._lib.scan_split_plan(3, 1, 8192, 72, bm._lib.BF16 if dtype == torch.bfloat16 else bm._lib.F32)[0]
+        assert auto == (8 if dtype == torch.bfloat16 else 1)
+        with torch.no_grad():
+            with bm._lib.tuning(bm._lib.TUNE_SCAN_SPLIT, 0 if dtype == torch.bfloat16 else 8):
+                out_split = bm.selective_scan_fn(*dev, delta_softplus=True)
+            with bm._lib.tuning(bm._lib.TUNE_SCAN_SPLIT, 1):
+                out_serial = bm.selective_scan_fn(*dev, delta_softplus=True)
+        assert rel(out_split, out_serial) < tol_pair
+        ref = orc.selective_scan_ref(*[t.double() for t in dev], delta_softplus=True)
+        assert rel(out_split, ref) < TOL[dtype]
+        assert rel(out_serial, ref) < TOL[dtype]
