@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (config 2: 64)")
     ap.add_argument("--frames", type=int, default=201)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-native-block", action="store_true",
+                    help="eager mode only: keep the block on the Python-sequenced autograd Function instead of the one-call "
+                         "native entry points (A/B of the two eager arrangements; a captured step always replays the former)")
     ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scan sweep points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -381,6 +384,8 @@ def run_ours(args, rank, world, local_rank):
         return bm.ops.mean_square_loss(out)          # mean(out^2) in fp32 (one launch forward, one backward)
 
     use_graph = not args.no_graph
+    if args.no_native_block:
+        bm.ops.USE_NATIVE_BLOCK = False
     if use_graph and not bucketed:
         runner = bm.GraphedTrainStep(fwd_loss, x_dev, zero_grad, opt, warmup=3)
 
@@ -422,12 +427,13 @@ def run_ours(args, rank, world, local_rank):
             opt.step()
             return loss
 
-    # count our own kernels in one eager step (the graph replays exactly these)
+    # count our own kernels in one eager step of the sequenced arrangement (the graph replays exactly these)
     bm._lib.launch_count = 0
-    zero_grad()
-    fwd_loss(x_dev).backward()
-    if bucketed and args.comm == "overlap":
-        bucket.finish_overlap()
+    with bm.ops.sequenced_block():
+        zero_grad()
+        fwd_loss(x_dev).backward()
+        if bucketed and args.comm == "overlap":
+            bucket.finish_overlap()
     torch.cuda.synchronize()
     launches_per_step = bm._lib.launch_count + (0 if args.torch_adamw else 2)   # + AdamW: step tick + update
 

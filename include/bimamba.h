@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define BIMAMBA_ABI_VERSION 10
+#define BIMAMBA_ABI_VERSION 11
 
 /* element types of activation operands */
 #define BIMAMBA_F32 0
@@ -384,6 +384,54 @@ size_t bimamba_block_bwd_workspace_bytes(int batch, int seqlen, int d_model, int
 int bimamba_block_fwd(const bimamba_block_desc* d, bimamba_stream_t stream);
 /* `d` is the descriptor the forward ran with (same workspace, save_for_backward != 0). */
 int bimamba_block_bwd(const bimamba_block_desc* d, const bimamba_block_grads* g, bimamba_stream_t stream);
+
+/* ---- The whole encoder layer in one call each way: PN_BiMambas_Encoder.forward (DualStreamSEMamba.py:467-486)
+ *   out = FFN(LN2(M(LN1 x) + flip(M(flip(LN1 x))))) + x,   FFN = Linear(d_model, d_ff) -> GELU (erf) -> Linear(d_ff, d_model)
+ * and its complete backward.  x / out / dout / dx have x_dtype: fp32 (the reference's autocast arrangement: fp32
+ * residual stream, 16-bit between the norms and up to the second feed-forward product) or the 16-bit compute dtype
+ * (= block.io_dtype).  `block` carries the Mamba weights, sizes, io_dtype and save_for_backward exactly as for
+ * bimamba_block_fwd; its x / out / workspace fields are ignored (the layer call sets them).  LayerNorm and feed-forward
+ * parameters are the fp32 masters (the call casts / transposes the two Linear weights itself, as the Python layer does
+ * every step).  d_model <= 1024; d_model, d_inner, d_ff multiples of 8.  Same kernels in the same order as the Python
+ * layer (encoder.py): bit-identical results. */
+typedef struct bimamba_layer_desc {
+  const void* x;           /* (batch, seqlen, d_model) x_dtype                                           */
+  void* out;               /* (batch, seqlen, d_model) x_dtype                                           */
+  const float* norm1_w;    /* (d_model) */
+  const float* norm1_b;
+  const float* norm2_w;
+  const float* norm2_b;
+  const float* ff_w1;      /* (d_ff, d_model)   feed_forward[0].weight                                   */
+  const float* ff_b1;      /* (d_ff)                                                                     */
+  const float* ff_w2;      /* (d_model, d_ff)   feed_forward[2].weight                                   */
+  const float* ff_b2;      /* (d_model)                                                                  */
+  bimamba_block_desc block;
+  void* workspace;         /* bimamba_layer_fwd_workspace_bytes(...) bytes, 256-byte aligned             */
+  size_t workspace_bytes;
+  float eps1, eps2;        /* LayerNorm epsilons                                                         */
+  int32_t d_ff, x_dtype;
+} bimamba_layer_desc;
+
+typedef struct bimamba_layer_grads {
+  const void* dout;        /* (batch, seqlen, d_model) x_dtype                                           */
+  void* dx;                /* (batch, seqlen, d_model) x_dtype                                           */
+  float* dnorm1;           /* (2, d_model) fp32: [dweight | dbias] of norm1                              */
+  float* dnorm2;           /* (2, d_model)                                                               */
+  float* dff_w1;           /* (d_ff, d_model)                                                            */
+  float* dff_b1;           /* (d_ff)                                                                     */
+  float* dff_w2;           /* (d_model, d_ff)                                                            */
+  float* dff_b2;           /* (d_model)                                                                  */
+  bimamba_block_grads block; /* transposed weight arrangements + the nine Mamba gradients; dout / dx / workspace ignored */
+  void* workspace;         /* scratch, bimamba_layer_bwd_workspace_bytes(...) bytes, 256-byte aligned    */
+  size_t workspace_bytes;
+} bimamba_layer_grads;
+
+size_t bimamba_layer_fwd_workspace_bytes(int batch, int seqlen, int d_model, int d_inner, int d_ff, int ndir, int io_dtype,
+                                         int save_for_backward);
+size_t bimamba_layer_bwd_workspace_bytes(int batch, int seqlen, int d_model, int d_inner, int d_ff, int d_conv, int ndir,
+                                         int io_dtype);
+int bimamba_layer_fwd(const bimamba_layer_desc* d, bimamba_stream_t stream);
+int bimamba_layer_bwd(const bimamba_layer_desc* d, const bimamba_layer_grads* g, bimamba_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ F32, BF16, F16 = 0, 1, 2
 FLAG_SOFTPLUS = 1
 FLAG_DTR_PADDED = 2
 FLAG_SILU = 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 CHUNK = 16
 
 EXPORTS = (
@@ -29,6 +29,7 @@ EXPORTS = (
     "bimamba_scan_fwd_workspace_bytes", "bimamba_scan_bwd_workspace_bytes", "bimamba_split3_bf16", "bimamba_cast", "bimamba_sumsq_slices", "bimamba_sumsq", "bimamba_scale_by",
     "bimamba_scan_fwd_split_plan", "bimamba_scan_fwd_split_workspace_bytes", "bimamba_selective_scan_fwd_split",
     "bimamba_block_fwd_workspace_bytes", "bimamba_block_bwd_workspace_bytes", "bimamba_block_fwd", "bimamba_block_bwd",
+    "bimamba_layer_fwd_workspace_bytes", "bimamba_layer_bwd_workspace_bytes", "bimamba_layer_fwd", "bimamba_layer_bwd",
 )
 
 
@@ -65,6 +66,23 @@ class BlockGrads(C.Structure):
         [(n, C.c_void_p) for n in ("dout", "dx", "WiT", "WxpT", "WoT", "WdT", "dW_in", "dconv_w", "dconv_b", "dW_x",
                                    "dW_dt", "db_dt", "dA_log", "dD", "dW_out", "workspace")]
         + [("workspace_bytes", C.c_size_t)]
+    )
+
+
+class LayerDesc(C.Structure):
+    """Mirror of `struct bimamba_layer_desc` (include/bimamba.h): the whole encoder layer, forward."""
+    _fields_ = (
+        [(n, C.c_void_p) for n in ("x", "out", "norm1_w", "norm1_b", "norm2_w", "norm2_b", "ff_w1", "ff_b1", "ff_w2", "ff_b2")]
+        + [("block", BlockDesc), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+           ("eps1", C.c_float), ("eps2", C.c_float), ("d_ff", C.c_int32), ("x_dtype", C.c_int32)]
+    )
+
+
+class LayerGrads(C.Structure):
+    """Mirror of `struct bimamba_layer_grads` (include/bimamba.h): the whole encoder layer, backward."""
+    _fields_ = (
+        [(n, C.c_void_p) for n in ("dout", "dx", "dnorm1", "dnorm2", "dff_w1", "dff_b1", "dff_w2", "dff_b2")]
+        + [("block", BlockGrads), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
     )
 
 
@@ -187,6 +205,14 @@ def load() -> C.CDLL:
         lib.bimamba_scan_fwd_split_workspace_bytes.argtypes = [i32, i32, i32, i32]
         lib.bimamba_selective_scan_fwd_split.restype = i32
         lib.bimamba_selective_scan_fwd_split.argtypes = [C.POINTER(ScanDesc), i32, i32, vp, C.c_size_t, vp]
+        lib.bimamba_layer_fwd_workspace_bytes.restype = C.c_size_t
+        lib.bimamba_layer_fwd_workspace_bytes.argtypes = [i32] * 8
+        lib.bimamba_layer_bwd_workspace_bytes.restype = C.c_size_t
+        lib.bimamba_layer_bwd_workspace_bytes.argtypes = [i32] * 8
+        lib.bimamba_layer_fwd.restype = i32
+        lib.bimamba_layer_fwd.argtypes = [C.POINTER(LayerDesc), vp]
+        lib.bimamba_layer_bwd.restype = i32
+        lib.bimamba_layer_bwd.argtypes = [C.POINTER(LayerDesc), C.POINTER(LayerGrads), vp]
         got = lib.bimamba_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError(f"libbimamba ABI {got} != expected {ABI_VERSION}; rebuild the library")

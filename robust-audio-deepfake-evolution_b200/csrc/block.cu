@@ -261,3 +261,204 @@ extern "C" int bimamba_block_bwd(const bimamba_block_desc* d, const bimamba_bloc
 #undef BIMAMBA_TRY
   return 0;
 }
+
+
+// ================================================================================================================
+// The whole encoder layer (PN_BiMambas_Encoder.forward, DualStreamSEMamba.py:467-486) in one call each way:
+//   out = FFN(LN2(M(LN1 x) + flip(M(flip(LN1 x))))) + x        FFN = Linear(d_model, d_ff) -> GELU (erf) -> Linear(d_ff, d_model)
+// Same kernels in the same order as the Python layer (encoder.py: layer_norm_fn -> BiMambaInnerFn -> layer_norm_fn ->
+// FeedForwardFn), so results are bit-identical to it; x / out / dout / dx may be fp32 (autocast: fp32 residual stream, the
+// 16-bit region between the norms and the feed-forward's second product) or the 16-bit dtype itself.
+// ================================================================================================================
+namespace bimamba {
+
+struct LayerFwdCarve {
+  size_t xn, mo, mn, h, a, stats, w1c, w1t, w2c, w2t, block, total;
+};
+
+static LayerFwdCarve carve_layer_fwd(int64_t B, int64_t L, int dm, int D, int dff, int ndir, int es, bool save) {
+  LayerFwdCarve c{};
+  const size_t M = (size_t)B * L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += up256(bytes); return o; };
+  c.xn = take(M * dm * es);
+  c.mo = take(M * dm * es);
+  c.mn = take(M * dm * es);
+  c.h = take(M * dff * es);
+  c.a = take(M * dff * es);
+  c.stats = take(M * 4 * 4);               // mean1 | rstd1 | mean2 | rstd2
+  c.w1c = take((size_t)dff * dm * es);
+  c.w1t = take((size_t)dff * dm * es);
+  c.w2c = take((size_t)dff * dm * es);
+  c.w2t = take((size_t)dff * dm * es);
+  c.block = off;
+  off += carve_fwd(B, L, D, ndir, es, save).total;
+  c.total = off;
+  return c;
+}
+
+struct LayerBwdCarve {
+  size_t g, da, dh, dmn, dmo, dxn, cs_part, ln_part, tn_part, block, total;
+  int cs_slices, ln_blocks;
+};
+
+static LayerBwdCarve carve_layer_bwd(int64_t B, int64_t L, int dm, int D, int dff, int K, int ndir, int es) {
+  LayerBwdCarve c{};
+  const size_t M = (size_t)B * L;
+  c.cs_slices = bimamba_colsum_slices((int64_t)M);
+  c.ln_blocks = bimamba_layernorm_bwd_blocks((int64_t)M);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += up256(bytes); return o; };
+  c.g = take(M * dm * es);
+  c.da = take(M * dff * es);
+  c.dh = take(M * dff * es);
+  c.dmn = take(M * dm * es);
+  c.dmo = take(M * dm * es);
+  c.dxn = take(M * dm * es);
+  c.cs_part = take((size_t)(c.cs_slices > 0 ? c.cs_slices : 1) * dff * 4);
+  c.ln_part = take((size_t)(c.ln_blocks > 0 ? c.ln_blocks : 1) * 2 * dm * 4);
+  size_t tn = (size_t)bimamba_gemm_tn_splits((int64_t)M, dm, dff) * dm * dff * 4;
+  const size_t tn2 = (size_t)bimamba_gemm_tn_splits((int64_t)M, dff, dm) * dm * dff * 4;
+  if (tn2 > tn) tn = tn2;
+  c.tn_part = take(tn);
+  c.block = off;
+  off += carve_bwd(B, L, dm, D, K, ndir, es).total;
+  c.total = off;
+  return c;
+}
+
+static int check_layer(const bimamba_layer_desc* d) {
+  if (!d) { set_err("layer: null descriptor"); return -1; }
+  const bimamba_block_desc& k = d->block;
+  if (k.batch < 0 || k.seqlen < 0 || k.d_model < 1 || k.d_inner < 1 || d->d_ff < 1) { set_err("layer: bad sizes"); return -3; }
+  if (k.io_dtype != BIMAMBA_BF16 && k.io_dtype != BIMAMBA_F16) { set_err("layer: the compute dtype must be bf16 or fp16"); return -6; }
+  if (d->x_dtype != BIMAMBA_F32 && d->x_dtype != k.io_dtype) { set_err("layer: x must be fp32 or the compute dtype"); return -6; }
+  if ((k.d_model & 7) || (k.d_inner & 7) || (d->d_ff & 7) || k.d_model > 1024) {
+    set_err("layer: d_model (<= 1024), d_inner and d_ff must be multiples of 8");
+    return -7;
+  }
+  if (!d->x || !d->out || !d->norm1_w || !d->norm1_b || !d->norm2_w || !d->norm2_b || !d->ff_w1 || !d->ff_b1 || !d->ff_w2 || !d->ff_b2) {
+    set_err("layer: null operand");
+    return -7;
+  }
+  if (!d->workspace || (reinterpret_cast<uintptr_t>(d->workspace) & 255) != 0) { set_err("layer: workspace missing or not 256-byte aligned"); return -7; }
+  return 0;
+}
+
+}  // namespace bimamba
+
+extern "C" size_t bimamba_layer_fwd_workspace_bytes(int batch, int seqlen, int d_model, int d_inner, int d_ff, int ndir,
+                                                    int io_dtype, int save_for_backward) {
+  (void)io_dtype;
+  if (batch <= 0 || seqlen <= 0 || d_model <= 0 || d_inner <= 0 || d_ff <= 0 || ndir <= 0) return 0;
+  return carve_layer_fwd(batch, seqlen, d_model, d_inner, d_ff, ndir, 2, save_for_backward != 0).total;
+}
+
+extern "C" size_t bimamba_layer_bwd_workspace_bytes(int batch, int seqlen, int d_model, int d_inner, int d_ff, int d_conv,
+                                                    int ndir, int io_dtype) {
+  (void)io_dtype;
+  if (batch <= 0 || seqlen <= 0 || d_model <= 0 || d_inner <= 0 || d_ff <= 0 || ndir <= 0 || d_conv <= 0) return 0;
+  return carve_layer_bwd(batch, seqlen, d_model, d_inner, d_ff, d_conv, ndir, 2).total;
+}
+
+extern "C" int bimamba_layer_fwd(const bimamba_layer_desc* d, bimamba_stream_t stream) {
+  int rc = check_layer(d);
+  if (rc) return rc;
+  bimamba_block_desc k = d->block;
+  if (k.batch == 0 || k.seqlen == 0) return 0;
+  const int es = 2, cd = k.io_dtype, xd = d->x_dtype;
+  const int64_t B = k.batch, L = k.seqlen, M = B * L;
+  const int dm = k.d_model, D = k.d_inner, dff = d->d_ff, nd = k.ndir;
+  const bool save = k.save_for_backward != 0;
+  const LayerFwdCarve c = carve_layer_fwd(B, L, dm, D, dff, nd, es, save);
+  if (d->workspace_bytes < c.total) { set_err("layer_fwd: workspace too small (bimamba_layer_fwd_workspace_bytes)"); return -10; }
+  unsigned char* ws = static_cast<unsigned char*>(d->workspace);
+  void *xn = ws + c.xn, *mo = ws + c.mo, *mn = ws + c.mn, *h = ws + c.h, *a = ws + c.a;
+  float* st = reinterpret_cast<float*>(ws + c.stats);
+  float *mean1 = save ? st : nullptr, *rstd1 = save ? st + M : nullptr, *mean2 = save ? st + 2 * M : nullptr,
+        *rstd2 = save ? st + 3 * M : nullptr;
+#define BIMAMBA_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
+  // norm1, written in the compute dtype (DualStreamSEMamba.py:472)
+  BIMAMBA_TRY(bimamba_layernorm_fwd(d->x, d->norm1_w, d->norm1_b, xn, mean1, rstd1, M, dm, d->eps1, xd, cd, stream));
+  // the bidirectional block (:473-481)
+  k.x = xn;
+  k.out = mo;
+  k.workspace = ws + c.block;
+  k.workspace_bytes = d->workspace_bytes - c.block;
+  BIMAMBA_TRY(bimamba_block_fwd(&k, stream));
+  // norm2 (:482)
+  BIMAMBA_TRY(bimamba_layernorm_fwd(mo, d->norm2_w, d->norm2_b, mn, mean2, rstd2, M, dm, d->eps2, cd, cd, stream));
+  // feed-forward + residual (:483-485): weights cast (and transposed for the backward), two products with the bias and
+  // the residual in their epilogues, exact GELU in between
+  BIMAMBA_TRY(bimamba_cast_transpose(d->ff_w1, ws + c.w1c, ws + c.w1t, dff, dm, cd, stream));
+  BIMAMBA_TRY(bimamba_cast_transpose(d->ff_w2, ws + c.w2c, ws + c.w2t, dm, dff, cd, stream));
+  BIMAMBA_TRY(bimamba_gemm_nt(mn, dm, ws + c.w1c, dm, h, dff, d->ff_b1, nullptr, M, dff, dm, cd, cd, stream));
+  BIMAMBA_TRY(bimamba_gelu_fwd(h, a, M * dff, cd, stream));
+  BIMAMBA_TRY(bimamba_gemm_nt(a, dff, ws + c.w2c, dff, d->out, dm, d->ff_b2, d->x, M, dm, dff, cd, xd, stream));
+#undef BIMAMBA_TRY
+  return 0;
+}
+
+extern "C" int bimamba_layer_bwd(const bimamba_layer_desc* d, const bimamba_layer_grads* g, bimamba_stream_t stream) {
+  int rc = check_layer(d);
+  if (rc) return rc;
+  if (!g) { set_err("layer_bwd: null gradient descriptor"); return -1; }
+  if (!g->dout || !g->dx || !g->dnorm1 || !g->dnorm2 || !g->dff_w1 || !g->dff_b1 || !g->dff_w2 || !g->dff_b2) {
+    set_err("layer_bwd: null operand");
+    return -8;
+  }
+  bimamba_block_desc k = d->block;
+  if (!k.save_for_backward) { set_err("layer_bwd: the forward must run with save_for_backward"); return -9; }
+  if (!g->workspace || (reinterpret_cast<uintptr_t>(g->workspace) & 255) != 0) { set_err("layer_bwd: workspace missing or not 256-byte aligned"); return -7; }
+  const int es = 2, cd = k.io_dtype, xd = d->x_dtype;
+  const int64_t B = k.batch, L = k.seqlen, M = B * L;
+  const int dm = k.d_model, D = k.d_inner, dff = d->d_ff, nd = k.ndir, K = k.d_conv;
+  if (M == 0) { set_err("layer_bwd: empty batch"); return -3; }
+  const LayerFwdCarve c = carve_layer_fwd(B, L, dm, D, dff, nd, es, true);
+  const LayerBwdCarve w = carve_layer_bwd(B, L, dm, D, dff, K, nd, es);
+  if (d->workspace_bytes < c.total) { set_err("layer_bwd: forward workspace too small"); return -10; }
+  if (g->workspace_bytes < w.total) { set_err("layer_bwd: workspace too small (bimamba_layer_bwd_workspace_bytes)"); return -10; }
+  unsigned char* fs = static_cast<unsigned char*>(d->workspace);
+  unsigned char* bs = static_cast<unsigned char*>(g->workspace);
+  void *xn = fs + c.xn, *mo = fs + c.mo, *mn = fs + c.mn, *h = fs + c.h, *a = fs + c.a;
+  const float* st = reinterpret_cast<const float*>(fs + c.stats);
+  const float *mean1 = st, *rstd1 = st + M, *mean2 = st + 2 * M, *rstd2 = st + 3 * M;
+  void *da = bs + w.da, *dh = bs + w.dh, *dmn = bs + w.dmn, *dmo = bs + w.dmo, *dxn = bs + w.dxn;
+  float *cs_part = reinterpret_cast<float*>(bs + w.cs_part), *ln_part = reinterpret_cast<float*>(bs + w.ln_part),
+        *tn_part = reinterpret_cast<float*>(bs + w.tn_part);
+#define BIMAMBA_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
+  // feed-forward backward; its incoming gradient is also the residual branch's (added inside norm1's backward below)
+  const void* gy = g->dout;
+  if (xd != cd) {
+    BIMAMBA_TRY(bimamba_cast(g->dout, bs + w.g, M * dm, xd, cd, stream));
+    gy = bs + w.g;
+  }
+  BIMAMBA_TRY(bimamba_colsum(gy, cs_part, M, dm, dm, cd, stream));
+  BIMAMBA_TRY(bimamba_reduce_partials(cs_part, g->dff_b2, 1, w.cs_slices, dm, 0, dm, 0, BIMAMBA_F32, 0, stream));
+  BIMAMBA_TRY(bimamba_gemm_tn(gy, dm, a, dff, g->dff_w2, tn_part, M, dm, dff, cd, stream));
+  BIMAMBA_TRY(bimamba_gemm_nt(gy, dm, fs + c.w2t, dm, da, dff, nullptr, nullptr, M, dff, dm, cd, cd, stream));
+  BIMAMBA_TRY(bimamba_gelu_bwd(h, da, dh, M * dff, cd, stream));
+  BIMAMBA_TRY(bimamba_colsum(dh, cs_part, M, dff, dff, cd, stream));
+  BIMAMBA_TRY(bimamba_reduce_partials(cs_part, g->dff_b1, 1, w.cs_slices, dff, 0, dff, 0, BIMAMBA_F32, 0, stream));
+  BIMAMBA_TRY(bimamba_gemm_tn(dh, dff, mn, dm, g->dff_w1, tn_part, M, dff, dm, cd, stream));
+  BIMAMBA_TRY(bimamba_gemm_nt(dh, dff, fs + c.w1t, dff, dmn, dm, nullptr, nullptr, M, dm, dff, cd, cd, stream));
+  // norm2 backward
+  BIMAMBA_TRY(bimamba_layernorm_bwd(mo, dmn, d->norm2_w, mean2, rstd2, nullptr, dmo, ln_part, M, dm, cd, cd, stream));
+  BIMAMBA_TRY(bimamba_reduce_partials(ln_part, g->dnorm2, 1, w.ln_blocks, 2 * dm, 0, 2 * dm, 0, BIMAMBA_F32, 0, stream));
+  // the block
+  k.x = xn;
+  k.out = mo;
+  k.workspace = fs + c.block;
+  k.workspace_bytes = d->workspace_bytes - c.block;
+  bimamba_block_grads kg = g->block;
+  kg.dout = dmo;
+  kg.dx = dxn;
+  kg.workspace = bs + w.block;
+  kg.workspace_bytes = g->workspace_bytes - w.block;
+  BIMAMBA_TRY(bimamba_block_bwd(&k, &kg, stream));
+  // norm1 backward + the residual branch's gradient
+  BIMAMBA_TRY(bimamba_layernorm_bwd(d->x, dxn, d->norm1_w, mean1, rstd1, g->dout, g->dx, ln_part, M, dm, xd, cd, stream));
+  BIMAMBA_TRY(bimamba_reduce_partials(ln_part, g->dnorm1, 1, w.ln_blocks, 2 * dm, 0, 2 * dm, 0, BIMAMBA_F32, 0, stream));
+#undef BIMAMBA_TRY
+  return 0;
+}

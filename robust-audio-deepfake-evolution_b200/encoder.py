@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .mamba_simple import Mamba
-from .ops import feed_forward_fn, head_fwd, head_pool_fn, layer_norm_fn
+from .ops import encoder_layer_native, feed_forward_fn, head_fwd, head_pool_fn, layer_norm_fn, native_layer_ok
 
 
 class PN_BiMambas_Encoder(nn.Module):
@@ -27,6 +27,10 @@ class PN_BiMambas_Encoder(nn.Module):
         )
 
     def forward(self, x):
+        if native_layer_ok(x, self):
+            # eager mode: the whole layer in one native call each way (same kernels, same order, same bits; a captured
+            # step keeps the sequenced Functions below, which overlap the weight-gradient products on a second stream)
+            return encoder_layer_native(x, self)
         # :471-472; the residual branch leaves the LayerNorm Function as its second output, so its gradient is added to dx
         # inside the LayerNorm backward kernel (no separate autograd add)
         x_norm, residual = layer_norm_fn(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, with_residual=True)

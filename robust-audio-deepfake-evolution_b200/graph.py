@@ -10,6 +10,8 @@ from typing import Callable, Optional
 
 import torch
 
+from .ops import sequenced_block
+
 
 def _snapshot(optimizer):
     params = [p for g in optimizer.param_groups for p in g["params"]]
@@ -56,7 +58,7 @@ class GraphedTrainStep:
         snap = _snapshot(optimizer) if (optimizer is not None and restore_after_warmup) else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), sequenced_block():   # warm up what the capture records, not the eager fast path
             for _ in range(max(1, warmup)):          # lazy inits (cuBLAS handles, func attributes) happen here
                 zero_grad()
                 loss = step_fn(self.static_x)
@@ -135,7 +137,7 @@ class GraphedForward:
         self.static_x.copy_(example)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side), torch.no_grad():
+        with torch.cuda.stream(side), torch.no_grad(), sequenced_block():
             for _ in range(max(1, warmup)):
                 fn(self.static_x)
         torch.cuda.current_stream().wait_stream(side)

@@ -1041,14 +1041,71 @@ class BiMambaInnerFn(torch.autograd.Function):
                 dW_out.to(pdt[8]), None, None, None)
 
 
+# Eager mode (no CUDA-graph capture): the block runs through the one-call native entry points - the same kernels in the
+# same order, bit-identical results (tests/test_gpu_native_block.py), but one ctypes call each way instead of ~30 plus
+# their allocations: 0.45 ms against 1.25 ms per block forward + backward at batch 64 x 201 frames, where the Python
+# sequencing is host-bound (profiles/r2_native_block_eager.json).  Under capture the sequenced Function stays: it
+# overlaps the weight-gradient products with the data-gradient chain on a second stream.
+USE_NATIVE_BLOCK = True
+
+
+class sequenced_block:
+    """Context manager: keep the block on the sequenced autograd Function (the warm-up steps of a graph capture run
+    exactly what the capture will record; per-kernel timing; A/B tests of the two arrangements)."""
+
+    def __enter__(self):
+        global USE_NATIVE_BLOCK
+        self.old, USE_NATIVE_BLOCK = USE_NATIVE_BLOCK, False
+        return self
+
+    def __exit__(self, *a):
+        global USE_NATIVE_BLOCK
+        USE_NATIVE_BLOCK = self.old
+        return False
+
+
+def _native_block_ok(x, W_in, cdtype) -> bool:
+    return (USE_NATIVE_BLOCK and _lib.kernel_timer is None and cdtype in (torch.bfloat16, torch.float16)
+            and x.is_cuda and x.numel() > 0 and W_in.shape[1] % 8 == 0 and (W_in.shape[0] // 2) % 8 == 0
+            and not torch.cuda.is_current_stream_capturing())
+
+
+class BiMambaNativeFn(torch.autograd.Function):
+    """BiMambaInnerFn through bimamba_block_fwd / bimamba_block_bwd (csrc/block.cu): eager-mode fast path."""
+
+    @staticmethod
+    def forward(ctx, x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bidirectional, cdtype, needs_bwd=True):
+        with torch.autocast("cuda", enabled=False):
+            if A_log.shape[1] != D_STATE:
+                raise NotImplementedError("d_state must be 16 (the Phase-6 configuration)")
+            if W_dt.shape[1] > MAX_DT_RANK:
+                raise NotImplementedError("dt_rank must be <= 16")
+            nb = NativeBlock(x.detach().to(cdtype), W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out,
+                             bidirectional=bidirectional, save_for_backward=needs_bwd)
+            out, nb.out = nb.out, None          # the output must not be reachable from ctx (reference cycle)
+            if needs_bwd:
+                ctx.nb = nb
+                ctx.meta = (x.dtype, tuple(t.dtype for t in (W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out)))
+            return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xdt, pdt = ctx.meta
+        with torch.autocast("cuda", enabled=False):
+            grads = ctx.nb.backward(dout)
+        return (grads[0].to(xdt), *[g.to(d) for g, d in zip(grads[1:], pdt)], None, None, None)
+
+
 def bimamba_inner_fn(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bidirectional=True,
                      compute_dtype=None):
     """x (B, L, d_model) -> (B, L, d_model).  compute_dtype: activation dtype of the kernels and
     GEMMs (default: the autocast dtype when autocast is on, else x.dtype); scan state is fp32."""
     if compute_dtype is None:
         compute_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
-    return BiMambaInnerFn.apply(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bool(bidirectional),
-                                compute_dtype, _wants_grad(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out))
+    _require_cuda(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out)
+    fn = BiMambaNativeFn if _native_block_ok(x, W_in, compute_dtype) else BiMambaInnerFn
+    return fn.apply(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out, bool(bidirectional),
+                    compute_dtype, _wants_grad(x, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out))
 
 
 # ----------------------------------------------------------------------------------------
@@ -1091,6 +1148,7 @@ class NativeBlock:
         d.io_dtype, d.save_for_backward = _dt(x), int(save_for_backward)
         self.desc = d
         _lib.check(lib.bimamba_block_fwd(C.byref(d), _stream()), "bimamba_block_fwd")
+        _lib.launch_count += 4           # the call enqueues 5 kernels (3 GEMMs, conv, scan)
 
     def backward(self, dout):
         """-> (dx, dW_in, dconv_w, dconv_b, dW_x, dW_dt, db_dt, dA_log, dD, dW_out), fp32 parameter gradients in the
@@ -1112,5 +1170,133 @@ class NativeBlock:
         (g.dW_in, g.dconv_w, g.dconv_b, g.dW_x, g.dW_dt, g.db_dt, g.dA_log, g.dD, g.dW_out) = [_ptr(t) for t in grads]
         g.workspace, g.workspace_bytes = _ptr(ws), nbytes
         _lib.check(lib.bimamba_block_bwd(C.byref(self.desc), C.byref(g), _stream()), "bimamba_block_bwd")
+        _lib.launch_count += 19          # 20 kernels: 4 + 4 x 2 GEMMs, scan, conv, row sum, 4 partial sums, layout pass
         self._keep = (dout, ws)
         return (dx, *grads)
+
+
+# ----------------------------------------------------------------------------------------
+# the whole encoder layer through bimamba_layer_fwd / bimamba_layer_bwd (eager-mode fast path of
+# PN_BiMambas_Encoder.forward; bit-identical to layer_norm_fn -> bimamba_inner_fn -> layer_norm_fn -> feed_forward_fn)
+# ----------------------------------------------------------------------------------------
+class NativeLayer:
+    """One forward call of the native encoder layer: descriptor, saved-activation workspace, packed Mamba weights."""
+
+    def __init__(self, x, norm1_w, norm1_b, eps1, norm2_w, norm2_b, eps2, W1, b1, W2, b2, W_in, conv_w, conv_b, W_x, W_dt,
+                 b_dt, A_log, Dp, W_out, cdtype, save_for_backward=True):
+        _require_cuda(x, norm1_w, W1, W_in)
+        lib = _lib.load()
+        Bsz, L, dm = x.shape
+        D, R, dff = W_in.shape[0] // 2, W_dt.shape[1], W1.shape[0]
+        self.x = x.detach().contiguous()
+        self.shape = (Bsz, L, dm, D, R, dff)
+        self.cdtype = cdtype
+        self.packed = pack_weights(W_in.detach(), W_x.detach(), W_dt.detach(), A_log.detach(), W_out.detach(), 2, cdtype)
+        Wi, WiT, Wxp, WxpT, Wo2, WoT, WdT, A32 = self.packed
+        self.f32 = tuple(_f32c(t) for t in (W_dt, conv_w, conv_b, Dp, b_dt, norm1_w, norm1_b, norm2_w, norm2_b, W1, b1, W2, b2))
+        Wd32, cw32, cb32, D32, bdt32, n1w, n1b, n2w, n2b, W1f, b1f, W2f, b2f = self.f32
+        cw32 = cw32.reshape(D, -1)
+        self.K = K = cw32.shape[1]
+        cdt = _DT[cdtype]
+        nbytes = lib.bimamba_layer_fwd_workspace_bytes(Bsz, L, dm, D, dff, 2, cdt, int(save_for_backward))
+        self.ws = torch.empty((max(nbytes, 1),), device=x.device, dtype=torch.uint8)
+        self.out = torch.empty_like(self.x)
+        d = _lib.LayerDesc()
+        d.x, d.out = _ptr(self.x), _ptr(self.out)
+        d.norm1_w, d.norm1_b, d.norm2_w, d.norm2_b = _ptr(n1w), _ptr(n1b), _ptr(n2w), _ptr(n2b)
+        d.ff_w1, d.ff_b1, d.ff_w2, d.ff_b2 = _ptr(W1f), _ptr(b1f), _ptr(W2f), _ptr(b2f)
+        k = d.block
+        k.Wi, k.Wxp, k.Wo2 = _ptr(Wi), _ptr(Wxp), _ptr(Wo2)
+        k.Wdt, k.A, k.D, k.dt_bias, k.conv_w, k.conv_b = _ptr(Wd32), _ptr(A32), _ptr(D32), _ptr(bdt32), _ptr(cw32), _ptr(cb32)
+        k.batch, k.seqlen, k.d_model, k.d_inner, k.dt_rank, k.d_conv, k.ndir = Bsz, L, dm, D, R, K, 2
+        k.io_dtype, k.save_for_backward = cdt, int(save_for_backward)
+        d.workspace, d.workspace_bytes = _ptr(self.ws), nbytes
+        d.eps1, d.eps2, d.d_ff, d.x_dtype = float(eps1), float(eps2), dff, _dt(self.x)
+        self.desc = d
+        self._keep_fwd = (cw32,)
+        _lib.check(lib.bimamba_layer_fwd(C.byref(d), _stream()), "bimamba_layer_fwd")
+        _lib.launch_count += 11          # 12 kernels: 2 LayerNorm, 5 of the block, 2 weight casts, 2 GEMMs, GELU
+
+    def backward(self, dout):
+        """-> (dx, dnorm1 (2, dm), dnorm2 (2, dm), dW1, db1, dW2, db2, then the nine Mamba gradients in the order
+        W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, D, W_out)."""
+        lib = _lib.load()
+        Bsz, L, dm, D, R, dff = self.shape
+        K, N = self.K, D_STATE
+        Wi, WiT, Wxp, WxpT, Wo2, WoT, WdT, A32 = self.packed
+        dev, f32 = self.x.device, torch.float32
+        dout = dout.to(self.x.dtype).contiguous()
+        dx = torch.empty_like(self.x)
+        lg = [torch.empty(s, device=dev, dtype=f32) for s in ((2, dm), (2, dm), (dff, dm), (dff,), (dm, dff), (dm,))]
+        mg = [torch.empty(s, device=dev, dtype=f32) for s in
+              ((2 * D, dm), (D, 1, K), (D,), (R + 2 * N, D), (D, R), (D,), (D, N), (D,), (dm, D))]
+        nbytes = lib.bimamba_layer_bwd_workspace_bytes(Bsz, L, dm, D, dff, K, 2, _DT[self.cdtype])
+        ws = torch.empty((max(nbytes, 1),), device=dev, dtype=torch.uint8)
+        g = _lib.LayerGrads()
+        g.dout, g.dx = _ptr(dout), _ptr(dx)
+        (g.dnorm1, g.dnorm2, g.dff_w1, g.dff_b1, g.dff_w2, g.dff_b2) = [_ptr(t) for t in lg]
+        kg = g.block
+        kg.WiT, kg.WxpT, kg.WoT, kg.WdT = _ptr(WiT), _ptr(WxpT), _ptr(WoT), _ptr(WdT)
+        (kg.dW_in, kg.dconv_w, kg.dconv_b, kg.dW_x, kg.dW_dt, kg.db_dt, kg.dA_log, kg.dD, kg.dW_out) = [_ptr(t) for t in mg]
+        g.workspace, g.workspace_bytes = _ptr(ws), nbytes
+        _lib.check(lib.bimamba_layer_bwd(C.byref(self.desc), C.byref(g), _stream()), "bimamba_layer_bwd")
+        _lib.launch_count += 35          # 36 kernels: 20 of the block, 11 of the feed-forward, 2 x 2 of the norms, the cast of dout
+        self._keep = (dout, ws)
+        return (dx, *lg, *mg)
+
+
+class EncoderLayerNativeFn(torch.autograd.Function):
+    """PN_BiMambas_Encoder.forward (DualStreamSEMamba.py:467-486) as one native call each way."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, n2w, n2b, W1, b1, W2, b2, W_in, conv_w, conv_b, W_x, W_dt, b_dt, A_log, Dp, W_out,
+                eps1, eps2, cdtype, needs_bwd=True):
+        with torch.autocast("cuda", enabled=False):
+            if A_log.shape[1] != D_STATE:
+                raise NotImplementedError("d_state must be 16 (the Phase-6 configuration)")
+            if W_dt.shape[1] > MAX_DT_RANK:
+                raise NotImplementedError("dt_rank must be <= 16")
+            nl = NativeLayer(x, n1w, n1b, eps1, n2w, n2b, eps2, W1, b1, W2, b2, W_in, conv_w, conv_b, W_x, W_dt, b_dt,
+                             A_log, Dp, W_out, cdtype, save_for_backward=needs_bwd)
+            out, nl.out = nl.out, None          # the output must not be reachable from ctx (reference cycle)
+            if needs_bwd:
+                ctx.nl = nl
+                ctx.pdt = tuple(t.dtype for t in (n1w, n1b, n2w, n2b, W1, b1, W2, b2, W_in, conv_w, conv_b, W_x, W_dt, b_dt,
+                                                  A_log, Dp, W_out))
+            return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        with torch.autocast("cuda", enabled=False):
+            r = ctx.nl.backward(dout)
+        dx, dn1, dn2 = r[0], r[1], r[2]
+        grads = [dn1[0], dn1[1], dn2[0], dn2[1], *r[3:]]
+        return (dx.view(dout.shape), *[g.to(d) for g, d in zip(grads, ctx.pdt)], None, None, None, None)
+
+
+def native_layer_ok(x, layer) -> bool:
+    """Eager-mode fast path of the encoder layer: CUDA, no graph capture, a 16-bit compute dtype (autocast, or 16-bit x),
+    x in fp32 or that dtype, exact GELU, widths the kernels take."""
+    if not (USE_NATIVE_BLOCK and _lib.kernel_timer is None and x.is_cuda and x.dim() == 3 and x.numel() > 0):
+        return False
+    cd = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    ff = layer.feed_forward
+    if cd not in (torch.bfloat16, torch.float16) or x.dtype not in (torch.float32, cd):
+        return False
+    if not (len(ff) == 3 and isinstance(ff[0], torch.nn.Linear) and isinstance(ff[1], torch.nn.GELU)
+            and ff[1].approximate == "none" and isinstance(ff[2], torch.nn.Linear) and ff[0].bias is not None
+            and ff[2].bias is not None):
+        return False
+    dm = x.shape[-1]
+    m = layer.mamba
+    return (dm % 8 == 0 and dm <= 1024 and ff[0].out_features % 8 == 0 and m.d_inner % 8 == 0 and m.d_state == D_STATE
+            and m.dt_rank <= MAX_DT_RANK and not torch.cuda.is_current_stream_capturing())
+
+
+def encoder_layer_native(x, layer):
+    cd = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    m, ff = layer.mamba, layer.feed_forward
+    ps = (layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias, ff[0].weight, ff[0].bias,
+          ff[2].weight, ff[2].bias, m.in_proj.weight, m.conv1d.weight, m.conv1d.bias, m.x_proj.weight, m.dt_proj.weight,
+          m.dt_proj.bias, m.A_log, m.D, m.out_proj.weight)
+    return EncoderLayerNativeFn.apply(x, *ps, layer.norm1.eps, layer.norm2.eps, cd, _wants_grad(x, *ps))

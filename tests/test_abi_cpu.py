@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol():
 
 
 @pytest.mark.parametrize("cname,mirror", [("bimamba_scan_desc", "ScanDesc"), ("bimamba_block_desc", "BlockDesc"),
-                                          ("bimamba_block_grads", "BlockGrads")])
+                                          ("bimamba_block_grads", "BlockGrads"), ("bimamba_layer_desc", "LayerDesc"),
+                                          ("bimamba_layer_grads", "LayerGrads")])
 def test_struct_layouts_match_header(tmp_path, cname, mirror):
     """sizeof / offsetof of the ctypes mirrors against the C compiler's view of the header."""
     cls = getattr(bm._lib, mirror)
@@ -216,3 +217,30 @@ def test_time_split_plan_and_errors_host_side():
     assert lib.bimamba_selective_scan_fwd_split(C.byref(d), 2, 64, None, 0, None) == -10      # no carry workspace
     assert b"carry workspace" in lib.bimamba_last_error()
     assert lib.bimamba_selective_scan_fwd_split(None, 2, 64, None, 0, None) == -1
+
+
+def test_native_layer_entry_points_host_side():
+    """bimamba_layer_fwd / bimamba_layer_bwd (the whole encoder layer in one call each way): the workspaces contain the
+    block's, argument errors are codes."""
+    lib = bm._lib.load()
+    B, L, dm, D, dff, ndir, K = 64, 201, 144, 288, 576, 2, 4
+    up = lambda v: (v + 255) // 256 * 256
+    M, es = B * L, 2
+    own = 3 * up(M * dm * es) + 2 * up(M * dff * es) + up(M * 16) + 4 * up(dff * dm * es)
+    for save in (0, 1):
+        assert lib.bimamba_layer_fwd_workspace_bytes(B, L, dm, D, dff, ndir, bm._lib.BF16, save) == (
+            own + lib.bimamba_block_fwd_workspace_bytes(B, L, dm, D, ndir, bm._lib.BF16, save))
+    bwd = lib.bimamba_layer_bwd_workspace_bytes(B, L, dm, D, dff, K, ndir, bm._lib.BF16)
+    assert bwd > lib.bimamba_block_bwd_workspace_bytes(B, L, dm, D, K, ndir, bm._lib.BF16) + 4 * M * dm * es + 2 * M * dff * es
+    assert bwd % 256 == 0 and lib.bimamba_layer_bwd_workspace_bytes(0, L, dm, D, dff, K, ndir, bm._lib.BF16) == 0
+    assert lib.bimamba_layer_fwd(None, None) == -1
+    d = bm._lib.LayerDesc()
+    k = d.block
+    k.batch, k.seqlen, k.d_model, k.d_inner, k.dt_rank, k.d_conv, k.ndir, k.io_dtype = 2, 5, 144, 288, 9, 4, 2, bm._lib.BF16
+    d.d_ff, d.x_dtype = 576, bm._lib.F16
+    assert lib.bimamba_layer_fwd(C.byref(d), None) == -6                   # x must be fp32 or the compute dtype
+    d.x_dtype = bm._lib.F32
+    assert lib.bimamba_layer_fwd(C.byref(d), None) == -7                   # null operands
+    d.d_ff = 100
+    assert lib.bimamba_layer_fwd(C.byref(d), None) == -7                   # d_ff must be a multiple of 8
+    assert lib.bimamba_layer_bwd(C.byref(d), None, None) < 0

@@ -39,11 +39,22 @@ def test_native_block_equals_autograd_function_bitwise(d_model, Bsz, L, bidir, d
     g = torch.Generator().manual_seed(L)
     x = torch.randn(Bsz, L, d_model, generator=g).cuda().to(dtype)
     cot = torch.randn(Bsz, L, d_model, generator=g).cuda().to(dtype)
-    # Python product path
+    # Python product path, both of its arrangements
     wp = [t.clone().requires_grad_(True) for t in w]
     xp = x.clone().requires_grad_(True)
-    out_p = ops.bimamba_inner_fn(xp, *wp, bidirectional=bidir, compute_dtype=dtype)
-    out_p.backward(cot)
+    with ops.sequenced_block():               # the sequenced autograd Function (what a captured step replays)
+        out_p = ops.bimamba_inner_fn(xp, *wp, bidirectional=bidir, compute_dtype=dtype)
+        assert "BiMambaInnerFn" in type(out_p.grad_fn).__name__
+        out_p.backward(cot)
+    # eager default: the same call goes through the native entry points, same bits
+    we = [t.clone().requires_grad_(True) for t in w]
+    xe = x.clone().requires_grad_(True)
+    out_e = ops.bimamba_inner_fn(xe, *we, bidirectional=bidir, compute_dtype=dtype)
+    assert "BiMambaNativeFn" in type(out_e.grad_fn).__name__
+    out_e.backward(cot)
+    assert torch.equal(out_e, out_p) and torch.equal(xe.grad, xp.grad)
+    for a, b in zip(we, wp):
+        assert torch.equal(a.grad, b.grad)
     # native one-call path
     nb = ops.NativeBlock(x, *w, bidirectional=bidir, save_for_backward=True)
     grads = nb.backward(cot)
@@ -90,3 +101,67 @@ def test_native_block_argument_errors_on_device():
     d.workspace_bytes = 16
     assert lib.bimamba_block_fwd(C.byref(d), None) == -10
     assert b"workspace too small" in lib.bimamba_last_error()
+
+
+@pytest.mark.parametrize("mode", ["autocast_bf16", "autocast_fp16", "pure_bf16"])
+@pytest.mark.parametrize("Bsz,L", [(3, 201), (2, 5)])
+def test_native_encoder_layer_equals_sequenced_layer_bitwise(mode, Bsz, L):
+    """PN_BiMambas_Encoder.forward in eager mode = bimamba_layer_fwd / bimamba_layer_bwd (one call each way); the
+    sequenced Functions (what a captured step replays) give the same bits: output, dx and all 17 parameter gradients."""
+    torch.manual_seed(7)
+    enc = bm.PN_BiMambas_Encoder(144, 16).cuda()
+    with torch.no_grad():
+        enc.mamba.A_log.add_(0.1 * torch.randn_like(enc.mamba.A_log))
+        enc.norm1.weight.add_(0.1 * torch.randn_like(enc.norm1.weight))
+        enc.norm2.bias.add_(0.1 * torch.randn_like(enc.norm2.bias))
+    x = torch.randn(Bsz, L, 144, device="cuda")
+    cot = torch.randn(Bsz, L, 144, device="cuda")
+    if mode == "pure_bf16":
+        x, cot = x.bfloat16(), cot.bfloat16()
+    ac = dict(device_type="cuda", dtype=torch.float16 if mode == "autocast_fp16" else torch.bfloat16,
+              enabled=mode != "pure_bf16")
+    runs = []
+    for native in (False, True):
+        for p in enc.parameters():
+            p.grad = None
+        xi = x.clone().requires_grad_(True)
+        if native:
+            with torch.autocast(**ac):
+                out = enc(xi)
+            assert "EncoderLayerNativeFn" in type(out.grad_fn).__name__
+        else:
+            with ops.sequenced_block(), torch.autocast(**ac):
+                out = enc(xi)
+            assert "EncoderLayerNativeFn" not in type(out.grad_fn).__name__
+        assert out.dtype == x.dtype
+        out.backward(cot)
+        torch.cuda.synchronize()
+        runs.append([out.detach().clone(), xi.grad.clone()] + [p.grad.clone() for p in enc.parameters()])
+    names = ["out", "dx"] + [n for n, _ in enc.named_parameters()]
+    for n, a, b in zip(names, *runs):
+        assert a.dtype == b.dtype and torch.equal(a, b), n
+    # scoring: no_grad forward through the native call (no statistics / checkpoints kept), same bits again
+    with torch.no_grad(), torch.autocast(**ac):
+        out_ng = enc(x)
+    assert torch.equal(out_ng, runs[0][0])
+
+
+def test_native_encoder_layer_vs_oracle_bf16():
+    """The native layer against the fp64 oracle of the reference's PN_BiMambas_Encoder (north_star: 2e-2 in bf16)."""
+    torch.manual_seed(3)
+    enc = bm.PN_BiMambas_Encoder(144, 16).cuda()
+    x = torch.randn(4, 201, 144)
+    cot = torch.randn(4, 201, 144)
+    pr = {k: v.detach().double().cpu().requires_grad_(True) for k, v in enc.state_dict().items()}
+    xr = x.double().requires_grad_(True)
+    ref = orc.pn_bimamba_encoder_ref(pr, xr)
+    (ref * cot.double()).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = enc(xd)
+    assert "EncoderLayerNativeFn" in type(out.grad_fn).__name__
+    out.backward(cot.cuda())
+    assert rel(out, ref) < 2e-2
+    assert rel(xd.grad, xr.grad) < 2e-2
+    for name, p in enc.named_parameters():
+        assert rel(p.grad, pr[name].grad) < 2e-2, name
