@@ -544,7 +544,8 @@ def run_ours(args, rank, world, local_rank):
             "steps": K, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args, world), l2="flushed between steps (256 MB write, untimed); per-step CUDA events summed",
-                           launch="CUDA-graph replay" if use_graph else "eager", state="fp32", weights="fp32 master, bf16 autocast",
+                           launch="CUDA-graph replay" if use_graph else ("eager, native one-call layer entry points" if bm.ops.USE_NATIVE_BLOCK
+                                                                          else "eager, Python-sequenced launches"), state="fp32", weights="fp32 master, bf16 autocast",
                            gemm="tcgen05 (this repo)",
                            comm=(None if world == 1 else {"overlap": "NCCL all-reduce (AVG) per encoder layer inside the step "
                                  "graph, overlapping the remaining backward",
