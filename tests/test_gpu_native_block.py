@@ -1,6 +1,8 @@
-"""The one-call native entry points bimamba_block_fwd / bimamba_block_bwd (include/bimamba.h; SURVEY 8b `conv_scan_bi` +
-projections) on the GPU: against the fp64 oracle (outputs and every gradient, bf16 tolerance 2e-2) and, bit for bit,
-against the Python autograd Function that sequences the same kernels (ops.py: BiMambaInnerFn)."""
+"""The one-call native entry points on the GPU (include/bimamba.h; csrc/block.cu):
+bimamba_block_fwd / bimamba_block_bwd (SURVEY 8b `conv_scan_bi` + projections) and bimamba_layer_fwd / bimamba_layer_bwd (the
+whole PN_BiMambas_Encoder layer) - against the fp64 oracle (outputs and every gradient, bf16 tolerance 2e-2) and, bit for
+bit, against the Python autograd Functions that sequence the same kernels (what a captured step replays).  In eager mode
+these calls ARE the product path of `bimamba_inner_fn` / `PN_BiMambas_Encoder.forward`."""
 import ctypes as C
 
 import pytest
