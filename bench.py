@@ -283,11 +283,15 @@ def scan_sweep(bm, peak):
             bm._lib.kernel_timer = None
             times["scan_fwd_infer"] = timer.summary()["scan_fwd"]
             es = 4 if dtype == torch.float32 else 2
+            nseg = bm._lib.scan_split_plan(Bsz, 1, L, D_INNER, bm._lib.F32 if dtype == torch.float32 else bm._lib.BF16)[0]
             for kname, bwd in (("scan_fwd_infer", False), ("scan_fwd", False), ("scan_bwd", True)):
                 ms = statistics.median(times[kname][2:])
                 gbs = scan_bytes(Bsz * L, 1, es, bwd) / (ms * 1e-3) / 1e9
-                out.append({"kernel": kname, "io": name, "L": L, "batch": Bsz, "ms": round(ms, 4),
-                            "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+                row = {"kernel": kname, "io": name, "L": L, "batch": Bsz, "ms": round(ms, 4),
+                       "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+                if nseg > 1 and not bwd:
+                    row["time_segments"] = nseg      # time-parallel forward: carry pass + output pass (two launches)
+                out.append(row)
             del u, delta, z, Bm, Cm, cot, o
             torch.cuda.empty_cache()
     return out
@@ -564,6 +568,11 @@ def run_ours(args, rank, world, local_rank):
             "roofline_more": roofline_more,
             "cpu_baseline": cpu,
             "scan_sweep": sweep,
+            "scan_sweep_note": ("config 5: single-direction selective_scan op, 524 288 frames, D 288, N 16; per point "
+                                "scan_fwd_infer = no-grad forward (the op-boundary bytes), scan_fwd = training forward (also writes "
+                                "the fp32 checkpoints every 8 steps and the ungated y), scan_bwd; frac = SURVEY 8(d) algorithmic "
+                                "bytes / kernel time / measured HBM peak; rows with time_segments ran the time-parallel forward "
+                                "(carry pass + output pass, both launches inside the timed interval)") if sweep else None,
             "loss": loss_val,
         }
         print(json.dumps(line), flush=True)
