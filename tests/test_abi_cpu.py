@@ -244,3 +244,50 @@ def test_native_layer_entry_points_host_side():
     d.d_ff = 100
     assert lib.bimamba_layer_fwd(C.byref(d), None) == -7                   # d_ff must be a multiple of 8
     assert lib.bimamba_layer_bwd(C.byref(d), None, None) < 0
+
+
+def test_header_is_plain_c_and_the_integration_example_compiles(tmp_path):
+    """include/bimamba.h is C99 (no C++ leaks into the boundary) and the host-side example of INTEGRATION.md section 4 - a C
+    program that fills the block / layer descriptors and calls the one-call entry points - compiles against it and links
+    against the library (gcc only; nothing is executed on a device)."""
+    prog = tmp_path / "host.c"
+    prog.write_text(f"""#include <stdio.h>
+#include "{HEADER}"
+int run_block(void* stream, const void* x, void* out, void* ws, size_t ws_bytes) {{
+  bimamba_block_desc d = {{0}};
+  d.x = x; d.out = out;
+  d.batch = 64; d.seqlen = 201; d.d_model = 144; d.d_inner = 288; d.dt_rank = 9; d.d_conv = 4; d.ndir = 2;
+  d.io_dtype = BIMAMBA_BF16; d.save_for_backward = 1;
+  d.workspace = ws; d.workspace_bytes = ws_bytes;
+  if (ws_bytes < bimamba_block_fwd_workspace_bytes(64, 201, 144, 288, 2, BIMAMBA_BF16, 1)) return -10;
+  int rc = bimamba_block_fwd(&d, stream);
+  if (rc) fprintf(stderr, "%s\\n", bimamba_last_error());
+  bimamba_block_grads g = {{0}};
+  g.workspace_bytes = bimamba_block_bwd_workspace_bytes(64, 201, 144, 288, 4, 2, BIMAMBA_BF16);
+  return rc ? rc : bimamba_block_bwd(&d, &g, stream);
+}}
+int run_layer(void* stream, const float* x, float* out) {{
+  bimamba_layer_desc l = {{0}};
+  l.x = x; l.out = out; l.eps1 = l.eps2 = 1e-5f; l.d_ff = 576; l.x_dtype = BIMAMBA_F32;
+  l.block.batch = 8; l.block.seqlen = 201; l.block.d_model = 144; l.block.d_inner = 288; l.block.dt_rank = 9;
+  l.block.d_conv = 4; l.block.ndir = 2; l.block.io_dtype = BIMAMBA_F16; l.block.save_for_backward = 1;
+  l.workspace_bytes = bimamba_layer_fwd_workspace_bytes(8, 201, 144, 288, 576, 2, BIMAMBA_F16, 1);
+  bimamba_layer_grads g = {{0}};
+  g.workspace_bytes = bimamba_layer_bwd_workspace_bytes(8, 201, 144, 288, 576, 4, 2, BIMAMBA_F16);
+  int rc = bimamba_layer_fwd(&l, stream);
+  return rc ? rc : bimamba_layer_bwd(&l, &g, stream);
+}}
+int main(void) {{
+  int nseg = 0, seg_len = 0;
+  bimamba_scan_fwd_split_plan(64, 1, 8192, 288, BIMAMBA_BF16, &nseg, &seg_len);
+  printf("%d %d %d %d\\n", bimamba_abi_version(), nseg, seg_len, run_layer(0, 0, 0));
+  return 0;
+}}
+""")
+    exe = tmp_path / "host"
+    lib = bm._lib.LIB_PATH
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", str(prog), "-o", str(exe), lib,
+                           "-Wl,-rpath," + os.path.dirname(lib)])
+    # argument validation only (null operands -> error code before any CUDA call): safe without a GPU
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert int(out[0]) == bm._lib.ABI_VERSION and (int(out[1]), int(out[2])) == (3, 2736) and int(out[3]) < 0
