@@ -11,6 +11,12 @@ Public names mirror what the reference's path binds upstream:
 
 All arithmetic runs in the CUDA library (ops on CPU tensors raise: there is no fallback).
 
+Two arrangements of the same kernels, bit-identical in their results: outside CUDA-graph capture the block and the whole
+encoder layer go through the library's one-call entry points (``BiMambaNativeFn`` / ``EncoderLayerNativeFn`` ->
+bimamba_block_fwd/bwd, bimamba_layer_fwd/bwd: device-bound eager steps); under capture - and inside
+``sequenced_block()`` - the Functions below enqueue the kernels one by one and overlap the weight-gradient products on a
+second stream.
+
 Layout.  The kernels are channel-last: every activation is (batch, time, channel) with unit channel
 stride, the layout the projections produce and consume, so the block has no transposes.  Tensors
 that exist once per direction are stored (batch, time, dir, channel) and handed to the kernels as
