@@ -115,6 +115,53 @@ def selective_scan_ref(u: Tensor, delta: Tensor, A: Tensor, B: Tensor, C: Tensor
     return (y, h) if return_last_state else y
 
 
+def selective_scan_split_ref(u: Tensor, delta: Tensor, A: Tensor, B: Tensor, C: Tensor,
+                             D: Optional[Tensor] = None, z: Optional[Tensor] = None,
+                             delta_bias: Optional[Tensor] = None, delta_softplus: bool = False,
+                             seg_len: int = 16) -> Tensor:
+    """The same scan as selective_scan_ref, evaluated the way the time-parallel CUDA forward does it
+    (csrc/scan_fwd_split.cu): a carry pass gives every time segment's end state e_s from a ZERO state and its
+    S_s = sum_t delta_t; the state entering segment s is the scan's associative rule applied to the earlier carries in
+    order, h <- exp(A S_k) h + e_k for k < s (prod_t exp(delta_t A) = exp(A sum_t delta_t)); the output pass then walks the
+    segment from that state.  Serial loop it restates: mamba_block.py:92-117."""
+    dtype_in = u.dtype
+    wide = torch.float64 if u.dtype == torch.float64 else torch.float32
+    u_, d_ = u.to(wide), delta.to(wide)
+    if delta_bias is not None:
+        d_ = d_ + delta_bias.to(wide).view(1, -1, 1)
+    if delta_softplus:
+        d_ = F.softplus(d_)
+    A_, B_, C_ = A.to(wide), B.to(wide), C.to(wide)
+    Bsz, Dm, L = u_.shape
+    N = A_.shape[1]
+
+    def walk(h, t0, t1, emit):
+        ys = []
+        for t in range(t0, t1):
+            dt = d_[:, :, t].unsqueeze(-1)
+            h = torch.exp(dt * A_.unsqueeze(0)) * h + dt * B_[:, :, t].unsqueeze(1) * u_[:, :, t].unsqueeze(-1)
+            if emit:
+                ys.append((h * C_[:, :, t].unsqueeze(1)).sum(-1))
+        return h, ys
+
+    bounds = [(t0, min(L, t0 + seg_len)) for t0 in range(0, L, seg_len)]
+    zero = torch.zeros(Bsz, Dm, N, dtype=wide, device=u.device)
+    carries = [(walk(zero, t0, t1, False)[0], d_[:, :, t0:t1].sum(-1)) for t0, t1 in bounds[:-1]]      # carry pass
+    ys = []
+    for s_, (t0, t1) in enumerate(bounds):                                                              # output pass
+        h = zero
+        for e_k, S_k in carries[:s_]:
+            h = torch.exp(S_k.unsqueeze(-1) * A_.unsqueeze(0)) * h + e_k
+        ys += walk(h, t0, t1, True)[1]
+    y = torch.stack(ys, dim=2) if L > 0 else torch.zeros_like(u_)
+    if D is not None:
+        y = y + u_ * D.to(wide).view(1, -1, 1)
+    if z is not None:
+        zz = z.to(wide)
+        y = y * (zz * torch.sigmoid(zz))
+    return y.to(dtype_in)
+
+
 # --------------------------------------------------------------------------
 # block-level references
 # --------------------------------------------------------------------------
